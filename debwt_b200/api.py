@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's stage interface, on top of the C ABI.
+
+The reference exposes the hot path as a chain of C stage functions driven by main()
+(reference src/main.h:1-8, src/main.c:83-149).  `BwtBuilder` keeps that shape: set the FASTA
+records (collect), build (mySort .. sortBlue), fetch the three outputs (insertCase3), and
+`write_outputs` writes the reference's three files byte for byte (src/insertCase3.c:115-131).
+Everything that computes runs in libdebwt_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import numpy as np
+
+from . import binding
+from .binding import DebwtError, Stats, c_p, c_u64, check, lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(c_p)
+
+
+def join_records(records: Sequence) -> tuple[np.ndarray, np.ndarray]:
+    """T = S1 # S2 # ... Sn $ as one ASCII byte array + separator offsets (src/collect#$.c:56-90)."""
+    arrs = [np.frombuffer(r.encode() if isinstance(r, str) else bytes(r), dtype=np.uint8)
+            if not isinstance(r, np.ndarray) else r.astype(np.uint8, copy=False) for r in records]
+    if not arrs:
+        raise DebwtError("no records")
+    n = sum(a.size for a in arrs) + len(arrs)
+    text = np.empty(n, dtype=np.uint8)
+    seps = np.empty(len(arrs), dtype=np.uint64)
+    pos = 0
+    for i, a in enumerate(arrs):
+        text[pos:pos + a.size] = a
+        pos += a.size
+        text[pos] = ord("#")
+        seps[i] = pos
+        pos += 1
+    text[-1] = ord("$")
+    return text, seps
+
+
+class BwtBuilder:
+    """One context == one GPU (replaces the reference's process-wide state)."""
+
+    def __init__(self, device: int = 0, sort_config: int = 0):
+        self._h = c_p()
+        check(lib().debwt_create(ctypes.byref(self._h), device))
+        if sort_config:
+            lib().debwt_set_sort_config(self._h, sort_config)
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().debwt_destroy(self._h)
+            self._h = c_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- input -------------------------------------------------------------------------------
+    def set_records(self, records: Sequence):
+        """Per-record host buffers (what a kseq loop yields)."""
+        arrs = [np.ascontiguousarray(np.frombuffer(r.encode() if isinstance(r, str) else bytes(r), dtype=np.uint8)
+                                     if not isinstance(r, np.ndarray) else r, dtype=np.uint8) for r in records]
+        n = len(arrs)
+        ptrs = (c_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        lens = (c_u64 * max(n, 1))(*[a.size for a in arrs])
+        self._keep = arrs
+        check(lib().debwt_set_records(self._h, ptrs, lens, n))
+
+    def set_text(self, text: np.ndarray, seps: np.ndarray):
+        """One host buffer that already holds T (use pinned memory for the fastest H2D copy)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        seps = np.ascontiguousarray(seps, dtype=np.uint64)
+        self._keep = (text, seps)
+        check(lib().debwt_set_text(self._h, _ptr(text), text.size, _ptr(seps), seps.size))
+
+    def set_text_ptr(self, host_ptr: int, n_symbols: int, seps: np.ndarray):
+        seps = np.ascontiguousarray(seps, dtype=np.uint64)
+        self._keep = seps
+        check(lib().debwt_set_text(self._h, c_p(host_ptr), n_symbols, _ptr(seps), seps.size))
+
+    def set_text_device(self, device_ptr: int, n_symbols: int, seps: np.ndarray):
+        """T already resident in HBM (e.g. a torch.uint8 CUDA tensor's data_ptr())."""
+        seps = np.ascontiguousarray(seps, dtype=np.uint64)
+        self._keep = seps
+        check(lib().debwt_set_text_device(self._h, c_p(device_ptr), n_symbols, _ptr(seps), seps.size))
+
+    # -- build / output -------------------------------------------------------------------------
+    def build(self, k: int = 32):
+        check(lib().debwt_build(self._h, k))
+
+    def result(self, out_words: np.ndarray | None = None):
+        n, nw, ns = c_u64(), c_u64(), c_u64()
+        check(lib().debwt_result_sizes(self._h, ctypes.byref(n), ctypes.byref(nw), ctypes.byref(ns)))
+        words = out_words if out_words is not None else np.empty(nw.value, dtype=np.uint64)
+        sharp = np.empty(ns.value, dtype=np.uint64)
+        dollar = np.empty(1, dtype=np.uint64)
+        check(lib().debwt_result_copy(self._h, _ptr(words), _ptr(sharp), _ptr(dollar)))
+        return words, sharp, dollar
+
+    def result_into(self, host_ptr: int):
+        """Copy the packed BWT into caller-owned (e.g. pinned) host memory; returns (sharp, dollar)."""
+        n, nw, ns = c_u64(), c_u64(), c_u64()
+        check(lib().debwt_result_sizes(self._h, ctypes.byref(n), ctypes.byref(nw), ctypes.byref(ns)))
+        sharp = np.empty(ns.value, dtype=np.uint64)
+        dollar = np.empty(1, dtype=np.uint64)
+        check(lib().debwt_result_copy(self._h, c_p(host_ptr), _ptr(sharp), _ptr(dollar)))
+        return sharp, dollar
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().debwt_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+
+def build_bwt(records: Sequence, device: int = 0, k: int = 32):
+    """FASTA records in, (bwt_words, sharp_rows, dollar_row) out -- the whole hot path."""
+    with BwtBuilder(device) as b:
+        b.set_records(records)
+        b.build(k)
+        return b.result()
+
+
+def write_outputs(path: str, words: np.ndarray, sharp: np.ndarray, dollar: np.ndarray):
+    """The reference's three output files (src/insertCase3.c:115-131)."""
+    words.astype("<u8", copy=False).tofile(path)
+    sharp.astype("<u8", copy=False).tofile(path + ".#")
+    dollar.astype("<u8", copy=False).tofile(path + ".$")
+
+
+# ---- per-kernel entry points (parity tests) -------------------------------------------------------
+def k_pack(text: np.ndarray, device: int = 0) -> np.ndarray:
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    out = np.empty((text.size + 32 + 31) // 32, dtype=np.uint64)
+    check(lib().debwt_k_pack(device, _ptr(text), text.size, _ptr(out)))
+    return out
+
+
+def k_extract(text: np.ndarray, seps: np.ndarray, device: int = 0) -> np.ndarray:
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    seps = np.ascontiguousarray(seps, dtype=np.uint64)
+    out = np.empty(text.size - 32 * seps.size, dtype=np.uint64)
+    check(lib().debwt_k_extract(device, _ptr(text), text.size, _ptr(seps), seps.size, _ptr(out)))
+    return out
+
+
+def k_radix_sort(keys: np.ndarray, device: int = 0, cfg: int = 0):
+    k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    ms = ctypes.c_float()
+    check(lib().debwt_k_radix_sort_u64(device, _ptr(k), k.size, cfg, ctypes.byref(ms)))
+    return k, ms.value
+
+
+def k_rle(sorted_keys: np.ndarray, device: int = 0):
+    s = np.ascontiguousarray(sorted_keys, dtype=np.uint64)
+    km = np.empty(s.size, dtype=np.uint64)
+    ct = np.empty(s.size, dtype=np.uint64)
+    d = c_u64()
+    check(lib().debwt_k_rle(device, _ptr(s), s.size, _ptr(km), _ptr(ct), ctypes.byref(d)))
+    return km[:d.value].copy(), ct[:d.value].copy()
+
+
+def k_group_masks(text: np.ndarray, seps: np.ndarray, device: int = 0) -> np.ndarray:
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    seps = np.ascontiguousarray(seps, dtype=np.uint64)
+    out = np.empty(text.size - 32 * seps.size, dtype=np.uint16)
+    check(lib().debwt_k_group_masks(device, _ptr(text), text.size, _ptr(seps), seps.size, _ptr(out)))
+    return out
+
+
+def bench_sort(n: int, device: int = 0, cfg: int = 0, iters: int = 5) -> float:
+    ms = ctypes.c_float()
+    check(lib().debwt_bench_sort(device, n, cfg, iters, ctypes.byref(ms)))
+    return ms.value

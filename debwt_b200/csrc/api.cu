@@ -1,0 +1,709 @@
+// C ABI (include/debwt_b200.h) and the single-GPU build pipeline.
+//
+// Stage order mirrors the reference driver (reference src/main.c:83-149):
+//   mySort            -> K1 pack, K2 extract, K3 radix sort
+//   collect ‖ getKmer -> sentinel-window ("special") suffixes, K5/K6 edge marks
+//   generateBlocks    -> K7 branch table
+//   generateSP        -> K9 branch codes + blue entries
+//   sortBlue          -> K10 segmented sort
+//   insertCase3       -> K8 case-2 fill, K11 case-3 / special emission
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/debwt_b200.h"
+#include "radix_sort.cuh"
+#include "stages.cuh"
+
+namespace debwt {
+
+static thread_local std::string g_err;
+unsigned g_launches = 0;
+void set_error(const std::string& msg) { g_err = msg; }
+
+#define FAIL(msg)            \
+    do {                     \
+        debwt::set_error(msg); \
+        return -1;           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// stream-ordered device memory, cached by the driver pool between builds
+// ---------------------------------------------------------------------------------------------
+struct DevPool {
+    cudaStream_t st = nullptr;
+    std::vector<void*> live;
+    int alloc(void** p, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        CUDA_TRY(cudaMallocAsync(p, bytes, st));
+        live.push_back(*p);
+        return 0;
+    }
+    void release(void* p) {
+        if (!p) return;
+        auto it = std::find(live.begin(), live.end(), p);
+        if (it != live.end()) { live.erase(it); cudaFreeAsync(p, st); }
+    }
+    void release_all() {
+        for (void* p : live) cudaFreeAsync(p, st);
+        live.clear();
+    }
+};
+
+template <typename T>
+static int dalloc(DevPool& pool, T** p, size_t count) { return pool.alloc(reinterpret_cast<void**>(p), count * sizeof(T)); }
+
+struct Special {
+    u64 pos;
+    u32 j;        // bases before the separator (0..31)
+    u32 rec;
+    u64 ins, row;
+    u8 chr;
+    bool emit;
+};
+
+}  // namespace debwt
+
+using namespace debwt;
+
+struct debwt_ctx {
+    int device = 0;
+    int sort_cfg = 0;
+    cudaStream_t st = nullptr;
+    DevPool pool;
+    // input
+    u64 n = 0, n_rec = 0;
+    std::vector<u64> seps;
+    u8* d_ascii = nullptr;         // owned unless external
+    const u8* d_ascii_ext = nullptr;
+    // result
+    u64* d_bwt = nullptr;
+    u64* d_sharp = nullptr;
+    u32* d_sharp_count = nullptr;
+    u64* d_dollar = nullptr;
+    u64 n_words = 0;
+    bool built = false;
+    debwt_stats stats{};
+    cudaEvent_t ev[16]{};
+};
+
+namespace {
+
+std::mutex g_pool_mutex;
+
+int bind_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return 0;
+}
+
+int make_pool_sticky(int device) {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    cudaMemPool_t mp;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, device));
+    unsigned long long thr = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
+    return 0;
+}
+
+__global__ void write_seps_kernel(u8* text, const u64* seps, u64 n_rec) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rec) text[seps[r]] = (r + 1 == n_rec) ? '$' : '#';
+}
+
+__global__ void splitmix_fill_kernel(u64* keys, u64 n, u64 seed) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    keys[i] = z ^ (z >> 31);
+}
+
+template <typename T>
+int check_seps(const T* seps, u64 n_rec, u64 n) {
+    if (n_rec == 0) FAIL("no records");
+    if (n >= (1ull << 32) - 64) FAIL("text too long for one device in this build (n_symbols must be < 2^32 - 64)");
+    u64 start = 0;
+    for (u64 r = 0; r < n_rec; ++r) {
+        if (seps[r] < start || seps[r] - start <= 32) FAIL("Length <= 32!");      // src/collect#$.c:41-45
+        start = seps[r] + 1;
+    }
+    if (start != n) FAIL("last separator must be the last symbol");
+    return 0;
+}
+
+void reset_input(debwt_ctx* c) {
+    c->pool.release_all();
+    c->d_ascii = nullptr;
+    c->d_ascii_ext = nullptr;
+    c->d_bwt = nullptr;
+    c->d_sharp = nullptr;
+    c->d_sharp_count = nullptr;
+    c->d_dollar = nullptr;
+    c->built = false;
+    c->stats = debwt_stats{};
+}
+
+// ---------------------------------------------------------------------------------------------
+// sentinel-window suffixes on the host (reference src/collect#$.c:131-157, 228-311, 348-602)
+// ---------------------------------------------------------------------------------------------
+struct HostText {
+    const u64* w;
+    const std::vector<u64>* seps;
+    u64 rec_of(u64 p) const { return (u64)(std::lower_bound(seps->begin(), seps->end(), p) - seps->begin()); }
+};
+
+// true suffix order under A<C<G<T<#<$; equal '#' are compared through, '$' is largest
+// (reference cmp, src/collect#$.c:253-311)
+bool special_less(const HostText& t, u64 pa, u64 pb) {
+    if (pa == pb) return false;
+    const u64 R = t.seps->size();
+    u64 ra = t.rec_of(pa), rb = t.rec_of(pb);
+    for (;;) {
+        const u64 da = (*t.seps)[ra] - pa, db = (*t.seps)[rb] - pb;
+        const u64 m = da < db ? da : db;
+        for (u64 off = 0; off < m; off += 32) {
+            u64 wa = text_window32(t.w, pa + off), wb = text_window32(t.w, pb + off);
+            const u64 len = m - off;
+            if (len < 32) { const u64 mask = ~(~0ull >> (2 * len)); wa &= mask; wb &= mask; }
+            if (wa != wb) return wa < wb;
+        }
+        if (da != db) return da > db;            // the side that reaches its separator first is larger
+        const bool a_end = (ra + 1 == R), b_end = (rb + 1 == R);
+        if (a_end || b_end) return !a_end && b_end;
+        pa = (*t.seps)[ra] + 1; pb = (*t.seps)[rb] + 1;
+        ++ra; ++rb;
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+// ABI
+// =============================================================================================
+extern "C" {
+
+const char* debwt_last_error(void) { return g_err.c_str(); }
+
+int debwt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int debwt_create(debwt_ctx** out, int device) {
+    if (!out) FAIL("null out pointer");
+    if (debwt_device_count() <= device || device < 0) FAIL("no such CUDA device (this library has no CPU fallback)");
+    if (bind_device(device)) return -1;
+    if (make_pool_sticky(device)) return -1;
+    debwt_ctx* c = new debwt_ctx();
+    c->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    c->pool.st = c->st;
+    for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    *out = c;
+    return 0;
+}
+
+void debwt_destroy(debwt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->pool.release_all();
+    cudaStreamSynchronize(c->st);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int debwt_set_sort_config(debwt_ctx* c, int cfg) {
+    int old = c->sort_cfg;
+    c->sort_cfg = cfg;
+    return old;
+}
+
+int debwt_set_records(debwt_ctx* c, const char* const* seqs, const uint64_t* lens, uint64_t n_records) {
+    if (!c || !seqs || !lens) FAIL("null argument");
+    if (bind_device(c->device)) return -1;
+    reset_input(c);
+    if (n_records == 0) FAIL("no records");
+    u64 n = 0;
+    c->seps.resize(n_records);
+    for (u64 r = 0; r < n_records; ++r) {
+        if (lens[r] <= 32) FAIL("Length <= 32!");
+        n += lens[r];
+        c->seps[r] = n;
+        ++n;
+    }
+    if (check_seps(c->seps.data(), n_records, n)) return -1;
+    c->n = n; c->n_rec = n_records;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
+    if (dalloc(c->pool, &c->d_ascii, n + 64)) return -1;
+    u64 off = 0;
+    for (u64 r = 0; r < n_records; ++r) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_ascii + off, seqs[r], lens[r], cudaMemcpyHostToDevice, c->st));
+        off += lens[r] + 1;
+    }
+    u64* d_seps = nullptr;
+    if (dalloc(c->pool, &d_seps, n_records)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_seps, c->seps.data(), n_records * 8, cudaMemcpyHostToDevice, c->st));
+    write_seps_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, c->st>>>(c->d_ascii, d_seps, n_records);
+    CUDA_TRY(cudaGetLastError());
+    c->pool.release(d_seps);
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->st));
+    CUDA_TRY(cudaStreamSynchronize(c->st));
+    CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev[0], c->ev[1]));
+    return 0;
+}
+
+int debwt_set_text(debwt_ctx* c, const char* text, uint64_t n, const uint64_t* seps, uint64_t n_records) {
+    if (!c || !text || !seps) FAIL("null argument");
+    if (bind_device(c->device)) return -1;
+    reset_input(c);
+    if (check_seps(seps, n_records, n)) return -1;
+    c->seps.assign(seps, seps + n_records);
+    c->n = n; c->n_rec = n_records;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
+    if (dalloc(c->pool, &c->d_ascii, n + 64)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(c->d_ascii, text, n, cudaMemcpyHostToDevice, c->st));
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->st));
+    CUDA_TRY(cudaStreamSynchronize(c->st));
+    CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev[0], c->ev[1]));
+    return 0;
+}
+
+int debwt_set_text_device(debwt_ctx* c, const void* d_text, uint64_t n, const uint64_t* seps, uint64_t n_records) {
+    if (!c || !d_text || !seps) FAIL("null argument");
+    if (bind_device(c->device)) return -1;
+    reset_input(c);
+    if (check_seps(seps, n_records, n)) return -1;
+    if (reinterpret_cast<uintptr_t>(d_text) & 15) FAIL("device text must be 16-byte aligned");
+    c->seps.assign(seps, seps + n_records);
+    c->n = n; c->n_rec = n_records;
+    c->d_ascii_ext = reinterpret_cast<const u8*>(d_text);
+    return 0;
+}
+
+int debwt_build(debwt_ctx* c, int k) {
+    if (!c) FAIL("null context");
+    if (k < 12 || k > 32) FAIL("-k: k-mer length (from 12 to 32, default 32)");      // src/main.c:45-46
+    if (c->n == 0) FAIL("no input set");
+    if (bind_device(c->device)) return -1;
+    const u8* ascii = c->d_ascii_ext ? c->d_ascii_ext : c->d_ascii;
+    if (!ascii) FAIL("input was consumed by a previous build; set it again");
+    cudaStream_t st = c->st;
+    DevPool& pool = c->pool;
+    const u64 n = c->n, R = c->n_rec, nk = n - 32 * R;
+    debwt_stats& S = c->stats;
+    const float keep_h2d = S.ms_h2d;
+    S = debwt_stats{};
+    S.ms_h2d = keep_h2d;
+    S.n_symbols = n; S.n_records = R; S.n_keys = nk; S.n_special = 32 * R;
+    g_launches = 0;
+    int evi = 0;
+    auto mark = [&]() { cudaEventRecord(c->ev[evi++], st); };
+    mark();                                                                     // ev0
+
+    // ---- K1 pack ----
+    u64* d_seps = nullptr; u64* d_text = nullptr; u32* d_err = nullptr;
+    if (dalloc(pool, &d_seps, R) || dalloc(pool, &d_text, text_words(n)) || dalloc(pool, &d_err, 4)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_seps, c->seps.data(), R * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
+    if (k_pack(ascii, n, d_text, d_err, st)) return -1;
+    if (c->d_ascii) { pool.release(c->d_ascii); c->d_ascii = nullptr; }
+    mark();                                                                     // ev1
+
+    // ---- K2 extract ----
+    u64 *d_ka = nullptr, *d_kb = nullptr;
+    if (dalloc(pool, &d_ka, nk + 2) || dalloc(pool, &d_kb, nk + 2)) return -1;
+    if (k_extract(d_text, n, d_seps, R, d_ka, st)) return -1;
+    mark();                                                                     // ev2
+
+    // ---- K3 sort ----
+    void* d_sortws = nullptr;
+    if (pool.alloc(&d_sortws, sort_workspace_bytes(nk, c->sort_cfg))) return -1;
+    SortWorkspace ws;
+    sort_workspace_bind(ws, d_sortws, nk, c->sort_cfg);
+    const unsigned launches_before_sort = g_launches;
+    u64* d_keys = nullptr;
+    if (radix_sort_u64(d_ka, d_kb, nk, ws, st, &d_keys)) return -1;
+    S.sort_launches = g_launches - launches_before_sort;
+    pool.release(d_sortws);
+    pool.release(d_keys == d_ka ? d_kb : d_ka);
+    u32 h_err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    mark();                                                                     // ev3
+
+    // ---- K5/K6 edge marks, K7 branch table ----
+    u16* d_gmask = nullptr;
+    if (dalloc(pool, &d_gmask, nk + 2)) return -1;
+    CUDA_TRY(cudaMemsetAsync(d_gmask, 0, (nk + 2) * 2, st));
+    if (k_mark_edges(d_keys, nk, d_gmask, st)) return -1;
+    if (k_mark_heads_tails(d_text, d_seps, R, d_keys, nk, d_gmask, st)) return -1;
+    if (k_propagate(d_keys, nk, d_gmask, st)) return -1;
+    void* d_brws = nullptr; u64* d_tot = nullptr;
+    if (pool.alloc(&d_brws, branch_workspace_bytes(nk)) || dalloc(pool, &d_tot, 4)) return -1;
+    if (k_branch_count(d_keys, nk, d_gmask, d_brws, d_tot, st)) return -1;
+    u64 h_tot[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_err) FAIL("input contains a symbol other than A, C, G, T (either case)");
+    BranchTable bt;
+    bt.n_branch = h_tot[0]; bt.n_blue = h_tot[1];
+    S.n_branch = bt.n_branch; S.n_blue = bt.n_blue;
+    {
+        int bits = 8;
+        while (bits < 27 && (1ull << bits) < 2 * bt.n_branch) ++bits;
+        bt.bits = bits;
+    }
+    if (dalloc(pool, &bt.kmer, bt.n_branch + 1) || dalloc(pool, &bt.head, bt.n_branch + 1) ||
+        dalloc(pool, &bt.blue, bt.n_branch + 2) || dalloc(pool, &bt.cursor, bt.n_branch + 1) ||
+        dalloc(pool, &bt.bidx, (1ull << bt.bits) + 2))
+        return -1;
+    CUDA_TRY(cudaMemsetAsync(bt.cursor, 0, (bt.n_branch + 1) * 4, st));
+    if (k_branch_write(d_keys, nk, d_gmask, d_brws, bt, st)) return -1;
+    {
+        const u32 m32 = (u32)bt.n_blue;
+        CUDA_TRY(cudaMemcpyAsync(bt.blue + bt.n_branch, &m32, 4, cudaMemcpyHostToDevice, st));
+    }
+    if (k_branch_index(bt, st)) return -1;
+    pool.release(d_brws);
+    mark();                                                                     // ev4
+
+    // ---- sentinel-window suffixes (host sort of 32 R suffixes over the packed text) ----
+    const u64 nspec = 32 * R;
+    std::vector<u64> h_text(text_words(n));
+    CUDA_TRY(cudaMemcpyAsync(h_text.data(), d_text, h_text.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    HostText ht{h_text.data(), &c->seps};
+    std::vector<Special> sp(nspec);
+    for (u64 r = 0, t = 0; r < R; ++r)
+        for (u32 j = 0; j < 32; ++j, ++t) {
+            sp[t].pos = c->seps[r] - j; sp[t].j = j; sp[t].rec = (u32)r; sp[t].emit = false;
+        }
+    std::sort(sp.begin(), sp.end(), [&](const Special& a, const Special& b) { return special_less(ht, a.pos, b.pos); });
+    std::vector<u64> h_pads(nspec), h_ins(nspec);
+    for (u64 t = 0; t < nspec; ++t) {
+        const u32 j = sp[t].j;
+        const u64 w = text_window32(h_text.data(), sp[t].pos);
+        h_pads[t] = j ? ((w & ~(~0ull >> (2 * j))) | (~0ull >> (2 * j))) : ~0ull;   // T padding (src/collect#$.c:428-455)
+        sp[t].chr = (u8)text_symbol(h_text.data(), sp[t].pos - 1);
+    }
+    u64 *d_pads = nullptr, *d_ins = nullptr;
+    if (dalloc(pool, &d_pads, nspec) || dalloc(pool, &d_ins, nspec)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_pads, h_pads.data(), nspec * 8, cudaMemcpyHostToDevice, st));
+    if (k_special_insertion(d_keys, nk, d_pads, nspec, d_ins, st)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(h_ins.data(), d_ins, nspec * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<u64> h_rows(nspec);
+    std::vector<u8> h_chr(nspec);
+    for (u64 t = 0; t < nspec; ++t) {
+        if (sp[t].j == 0) h_ins[t] = nk;                  // suffixes that start with a separator are the last R rows
+        if (t && h_ins[t] < h_ins[t - 1]) FAIL("internal: special insertion points are not monotone");
+        sp[t].ins = h_ins[t];
+        sp[t].row = h_ins[t] + t;
+        h_rows[t] = sp[t].row;
+        h_chr[t] = sp[t].chr;
+    }
+    // which sentinel-window positions emit a branch code (divideKmer, src/collect#$.c:537-598):
+    // tails always (src/INandOut.c:260-266); windows holding '#' when their 31-symbol prefix occurs with
+    // >= 2 different next symbols.  Windows holding '$' are unique.
+    std::vector<u64> h_emit_pos, h_tail_pos(R);
+    {
+        std::map<std::tuple<u32, u64, u64>, std::vector<u64>> groups;
+        for (u64 t = 0; t < nspec; ++t) {
+            const u32 j = sp[t].j;
+            if (j == 31) { sp[t].emit = true; h_tail_pos[sp[t].rec] = sp[t].pos; continue; }
+            if (sp[t].rec + 1 == R) continue;
+            const u64 p = sp[t].pos;
+            const u64 before = j ? (text_window32(h_text.data(), p) & ~(~0ull >> (2 * j))) : 0;
+            const u64 after = text_window32(h_text.data(), p + j + 1) & ~(~0ull >> (2 * (30 - j)));   // 30-j bases (>=0)
+            groups[std::make_tuple(j, before, j == 30 ? 0 : after)].push_back(t);
+        }
+        for (auto& g : groups) {
+            if (g.second.size() < 2) continue;
+            u32 seen = 0;
+            for (u64 t : g.second) seen |= 1u << text_symbol(h_text.data(), sp[t].pos + 31);
+            if (seen & (seen - 1))
+                for (u64 t : g.second) sp[t].emit = true;
+        }
+        for (u64 t = 0; t < nspec; ++t) if (sp[t].emit) h_emit_pos.push_back(sp[t].pos);
+    }
+    u64 *d_rows = nullptr, *d_emit = nullptr, *d_tail = nullptr, *d_tail_idx = nullptr;
+    u8* d_chr = nullptr;
+    if (dalloc(pool, &d_rows, nspec) || dalloc(pool, &d_chr, nspec) || dalloc(pool, &d_emit, h_emit_pos.size() + 1) ||
+        dalloc(pool, &d_tail, R) || dalloc(pool, &d_tail_idx, R))
+        return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_rows, h_rows.data(), nspec * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_chr, h_chr.data(), nspec, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ins, h_ins.data(), nspec * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_emit, h_emit_pos.data(), h_emit_pos.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_tail, h_tail_pos.data(), R * 8, cudaMemcpyHostToDevice, st));
+    mark();                                                                     // ev5
+
+    // ---- K9 branch codes + blue entries ----
+    const u64 nbw = (n + 31) / 32;
+    u32 *d_mo = nullptr, *d_wp = nullptr;
+    u64* d_blue = nullptr;
+    void* d_scanws = nullptr;
+    if (dalloc(pool, &d_mo, nbw + 2) || dalloc(pool, &d_wp, nbw + 2) || dalloc(pool, &d_blue, bt.n_blue + 1) ||
+        pool.alloc(&d_scanws, scan_workspace_bytes(nbw)))
+        return -1;
+    CUDA_TRY(cudaMemsetAsync(d_mo, 0, (nbw + 2) * 4, st));
+    if (k_flag_positions(d_text, n, d_seps, R, bt, d_mo, d_blue, st)) return -1;
+    if (k_patch_bits(d_mo, d_emit, h_emit_pos.size(), st)) return -1;
+    if (scan_exclusive_u32(d_mo, d_wp, nbw, true, d_scanws, d_tot, st)) return -1;
+    u64 n_codes = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_codes, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    S.n_codes = n_codes;
+    const u64 ncw = n_codes / 32 + 3;
+    u64* d_codes = nullptr; u32* d_sep = nullptr;
+    if (dalloc(pool, &d_codes, ncw) || dalloc(pool, &d_sep, ncw + 1)) return -1;
+    CUDA_TRY(cudaMemsetAsync(d_codes, 0, ncw * 8, st));
+    CUDA_TRY(cudaMemsetAsync(d_sep, 0, (ncw + 1) * 4, st));
+    if (k_emit_codes(d_text, n, d_mo, d_wp, d_codes, st)) return -1;
+    if (k_mark_sep_codes(d_mo, d_wp, d_tail, R, d_sep, d_tail_idx, st)) return -1;
+    if (k_blue_fix(d_blue, bt.n_blue, d_mo, d_wp, st)) return -1;
+    u64 dollar_index = 0;
+    CUDA_TRY(cudaMemcpyAsync(&dollar_index, d_tail_idx + (R - 1), 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    mark();                                                                     // ev6
+
+    // ---- K10 segmented sort ----
+    u32* d_work = nullptr;
+    if (dalloc(pool, &d_work, bt.n_branch + 8)) return -1;
+    SpView spv{d_codes, d_sep, dollar_index, n_codes};
+    if (k_sort_blue(d_blue, bt, spv, d_work, st)) return -1;
+    mark();                                                                     // ev7
+
+    // ---- K8 + K11 emission ----
+    c->n_words = nbw;
+    if (dalloc(pool, &c->d_bwt, nbw + 1) || dalloc(pool, &c->d_sharp, R + 1) || dalloc(pool, &c->d_sharp_count, 4) ||
+        dalloc(pool, &c->d_dollar, 2))
+        return -1;
+    CUDA_TRY(cudaMemsetAsync(c->d_sharp_count, 0, 16, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_dollar, 0xff, 16, st));
+    if (k_fill_case2(d_gmask, nk, n, d_rows, nspec, c->d_bwt, st)) return -1;
+    if (k_emit_blue(d_blue, bt, d_ins, nspec, c->d_bwt, c->d_sharp, c->d_sharp_count, c->d_dollar, st)) return -1;
+    if (k_emit_special(d_rows, d_chr, nspec, c->d_bwt, st)) return -1;
+    mark();                                                                     // ev8
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+
+    // free everything except the result
+    for (void* p : {(void*)d_seps, (void*)d_text, (void*)d_err, (void*)d_keys, (void*)d_gmask, (void*)d_tot,
+                    (void*)bt.kmer, (void*)bt.head, (void*)bt.blue, (void*)bt.cursor, (void*)bt.bidx, (void*)d_pads,
+                    (void*)d_ins, (void*)d_rows, (void*)d_chr, (void*)d_emit, (void*)d_tail, (void*)d_tail_idx,
+                    (void*)d_mo, (void*)d_wp, (void*)d_blue, d_scanws, (void*)d_codes, (void*)d_sep, (void*)d_work})
+        pool.release(p);
+
+    float* ms[] = {&S.ms_pack, &S.ms_extract, &S.ms_sort, &S.ms_classify, &S.ms_special, &S.ms_codes, &S.ms_bluesort, &S.ms_emit};
+    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventElapsedTime(ms[i], c->ev[i], c->ev[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&S.ms_total, c->ev[0], c->ev[8]));
+    S.total_launches = g_launches;
+    c->built = true;
+    return 0;
+}
+
+int debwt_result_sizes(const debwt_ctx* c, uint64_t* n_symbols, uint64_t* n_words, uint64_t* n_sharp) {
+    if (!c || !c->built) FAIL("no result: call debwt_build first");
+    if (n_symbols) *n_symbols = c->n;
+    if (n_words) *n_words = c->n_words;
+    if (n_sharp) *n_sharp = c->n_rec - 1;
+    return 0;
+}
+
+int debwt_result_copy(debwt_ctx* c, uint64_t* bwt_words, uint64_t* sharp_rows, uint64_t* dollar_row) {
+    if (!c || !c->built) FAIL("no result: call debwt_build first");
+    if (bind_device(c->device)) return -1;
+    CUDA_TRY(cudaEventRecord(c->ev[9], c->st));
+    if (bwt_words) CUDA_TRY(cudaMemcpyAsync(bwt_words, c->d_bwt, c->n_words * 8, cudaMemcpyDeviceToHost, c->st));
+    u32 cnt = 0;
+    CUDA_TRY(cudaMemcpyAsync(&cnt, c->d_sharp_count, 4, cudaMemcpyDeviceToHost, c->st));
+    u64 dol = 0;
+    CUDA_TRY(cudaMemcpyAsync(&dol, c->d_dollar, 8, cudaMemcpyDeviceToHost, c->st));
+    std::vector<u64> sharp(c->n_rec + 1);
+    CUDA_TRY(cudaMemcpyAsync(sharp.data(), c->d_sharp, (c->n_rec + 1) * 8, cudaMemcpyDeviceToHost, c->st));
+    CUDA_TRY(cudaEventRecord(c->ev[10], c->st));
+    CUDA_TRY(cudaStreamSynchronize(c->st));
+    CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_d2h, c->ev[9], c->ev[10]));
+    if (cnt != c->n_rec - 1) FAIL("internal: wrong number of '#' rows");
+    if (dol == ~0ull) FAIL("internal: '$' row missing");
+    std::sort(sharp.begin(), sharp.begin() + cnt);                      // ascending (src/insertCase3.c:84-95)
+    if (sharp_rows) std::copy(sharp.begin(), sharp.begin() + cnt, sharp_rows);
+    if (dollar_row) *dollar_row = dol;
+    return 0;
+}
+
+int debwt_get_stats(const debwt_ctx* c, debwt_stats* out) {
+    if (!c || !out) FAIL("null argument");
+    *out = c->stats;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel entry points
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Scratch {
+    cudaStream_t st = nullptr;
+    std::vector<void*> ptrs;
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+        if (st) cudaStreamDestroy(st);
+    }
+    template <typename T>
+    int get(T** p, size_t count) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T)));
+        ptrs.push_back(*p);
+        return 0;
+    }
+};
+int open_scratch(Scratch& s, int device) {
+    if (debwt_device_count() <= device || device < 0) FAIL("no such CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int debwt_k_pack(int device, const char* text, uint64_t n, uint64_t* words_out) {
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    u8* d_a; u64* d_w; u32* d_e;
+    if (s.get(&d_a, n + 64) || s.get(&d_w, text_words(n)) || s.get(&d_e, 4)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_a, text, n, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemsetAsync(d_e, 0, 16, s.st));
+    if (k_pack(d_a, n, d_w, d_e, s.st)) return -1;
+    u32 e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, d_e, 4, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaMemcpyAsync(words_out, d_w, ((n + 32 + 31) / 32) * 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    if (e) FAIL("input contains a symbol other than A, C, G, T (either case)");
+    return 0;
+}
+
+int debwt_k_extract(int device, const char* text, uint64_t n, const uint64_t* seps, uint64_t R, uint64_t* keys_out) {
+    if (check_seps(seps, R, n)) return -1;
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    const u64 nk = n - 32 * R;
+    u8* d_a; u64 *d_w, *d_s, *d_k; u32* d_e;
+    if (s.get(&d_a, n + 64) || s.get(&d_w, text_words(n)) || s.get(&d_e, 4) || s.get(&d_s, R) || s.get(&d_k, nk)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_a, text, n, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(d_s, seps, R * 8, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemsetAsync(d_e, 0, 16, s.st));
+    if (k_pack(d_a, n, d_w, d_e, s.st) || k_extract(d_w, n, d_s, R, d_k, s.st)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(keys_out, d_k, nk * 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    return 0;
+}
+
+int debwt_k_radix_sort_u64(int device, uint64_t* keys, uint64_t n, int cfg, float* ms_out) {
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    u64 *d_a, *d_b; void* d_ws;
+    if (s.get(&d_a, n + 2) || s.get(&d_b, n + 2)) return -1;
+    CUDA_TRY(cudaMalloc(&d_ws, sort_workspace_bytes(n, cfg)));
+    s.ptrs.push_back(d_ws);
+    SortWorkspace ws;
+    sort_workspace_bind(ws, d_ws, n, cfg);
+    CUDA_TRY(cudaMemcpyAsync(d_a, keys, n * 8, cudaMemcpyHostToDevice, s.st));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, s.st));
+    u64* res = nullptr;
+    if (radix_sort_u64(d_a, d_b, n, ws, s.st, &res)) return -1;
+    CUDA_TRY(cudaEventRecord(e1, s.st));
+    CUDA_TRY(cudaMemcpyAsync(keys, res, n * 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+int debwt_k_rle(int device, const uint64_t* sorted, uint64_t n, uint64_t* kmers_out, uint64_t* counts_out,
+                uint64_t* n_distinct_out) {
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    u64 *d_k, *d_km, *d_ct, *d_tot; void* d_ws;
+    if (s.get(&d_k, n + 2) || s.get(&d_km, n + 2) || s.get(&d_ct, n + 2) || s.get(&d_tot, 2)) return -1;
+    CUDA_TRY(cudaMalloc(&d_ws, rle_workspace_bytes(n)));
+    s.ptrs.push_back(d_ws);
+    CUDA_TRY(cudaMemcpyAsync(d_k, sorted, n * 8, cudaMemcpyHostToDevice, s.st));
+    if (k_rle(d_k, n, d_km, d_ct, d_ws, d_tot, s.st)) return -1;
+    u64 d = 0;
+    CUDA_TRY(cudaMemcpyAsync(&d, d_tot, 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    CUDA_TRY(cudaMemcpyAsync(kmers_out, d_km, d * 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaMemcpyAsync(counts_out, d_ct, d * 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    if (n_distinct_out) *n_distinct_out = d;
+    return 0;
+}
+
+int debwt_k_group_masks(int device, const char* text, uint64_t n, const uint64_t* seps, uint64_t R, uint16_t* masks_out) {
+    if (check_seps(seps, R, n)) return -1;
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    const u64 nk = n - 32 * R;
+    u8* d_a; u64 *d_w, *d_s, *d_ka, *d_kb; u32* d_e; u16* d_g; void* d_ws;
+    if (s.get(&d_a, n + 64) || s.get(&d_w, text_words(n)) || s.get(&d_e, 4) || s.get(&d_s, R) || s.get(&d_ka, nk + 2) ||
+        s.get(&d_kb, nk + 2) || s.get(&d_g, nk + 2))
+        return -1;
+    CUDA_TRY(cudaMalloc(&d_ws, sort_workspace_bytes(nk, 0)));
+    s.ptrs.push_back(d_ws);
+    SortWorkspace ws;
+    sort_workspace_bind(ws, d_ws, nk, 0);
+    CUDA_TRY(cudaMemcpyAsync(d_a, text, n, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(d_s, seps, R * 8, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemsetAsync(d_e, 0, 16, s.st));
+    CUDA_TRY(cudaMemsetAsync(d_g, 0, (nk + 2) * 2, s.st));
+    u64* d_keys = nullptr;
+    if (k_pack(d_a, n, d_w, d_e, s.st) || k_extract(d_w, n, d_s, R, d_ka, s.st) ||
+        radix_sort_u64(d_ka, d_kb, nk, ws, s.st, &d_keys) || k_mark_edges(d_keys, nk, d_g, s.st) ||
+        k_mark_heads_tails(d_w, d_s, R, d_keys, nk, d_g, s.st) || k_propagate(d_keys, nk, d_g, s.st))
+        return -1;
+    CUDA_TRY(cudaMemcpyAsync(masks_out, d_g, nk * 2, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    return 0;
+}
+
+int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out) {
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    u64 *d_a, *d_b; void* d_ws;
+    if (s.get(&d_a, n + 2) || s.get(&d_b, n + 2)) return -1;
+    CUDA_TRY(cudaMalloc(&d_ws, sort_workspace_bytes(n, cfg)));
+    s.ptrs.push_back(d_ws);
+    SortWorkspace ws;
+    sort_workspace_bind(ws, d_ws, n, cfg);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    float total = 0;
+    for (int it = 0; it < iters + 1; ++it) {
+        splitmix_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(d_a, n, 1234 + it);
+        CUDA_TRY(cudaEventRecord(e0, s.st));
+        u64* res = nullptr;
+        if (radix_sort_u64(d_a, d_b, n, ws, s.st, &res)) return -1;
+        CUDA_TRY(cudaEventRecord(e1, s.st));
+        CUDA_TRY(cudaStreamSynchronize(s.st));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (it) total += ms;                         // first run is warm-up
+    }
+    if (ms_out) *ms_out = total / (iters > 0 ? iters : 1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// K3: LSD radix sort of 64-bit (k+1)-mer keys -- the named roofline phase.
+//
+// Replaces the reference's bucket-by-12-bases + per-bucket qsort (reference src/mySort.c:98-176,
+// multiDistri :371-401, multiThreadSort :203-238, cmpKmer :338-345).
+//
+// Design (sm_100a, HBM bound, no tensor cores):
+//   * one histogram sweep builds all eight 256-bin digit histograms in shared memory (8 B/key read);
+//   * eight "onesweep" passes, each reading every key once and writing it once (16 B/key):
+//       - a tile of THREADS*ITEMS keys is loaded warp-striped (coalesced 256 B per warp load);
+//       - keys are ranked inside the warp with match.any (warp-ballot ranking) against a per-warp
+//         shared-memory digit histogram;
+//       - per-digit tile totals are chained across tiles by decoupled look-back (one 64-bit word
+//         carries status + epoch + value, so no fences and no reset between passes);
+//       - the tile is reordered in shared memory and written out bin by bin, so every warp store
+//         covers contiguous addresses.
+//   Algorithmic traffic: 8 + 8*16 = 136 B/key.
+#include "radix_sort.cuh"
+
+namespace debwt {
+
+namespace {
+
+constexpr int RADIX = 256;
+constexpr int PASSES = 8;
+constexpr u64 LB_VALUE_MASK = (1ull << 56) - 1;
+constexpr u64 LB_EPOCH_MASK = 63ull << 56;
+constexpr u64 LB_AGG = 1ull << 62;
+constexpr u64 LB_INCL = 2ull << 62;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n,
+                                                            u64* __restrict__ ghist) {
+    __shared__ u32 sh[PASSES * RADIX];
+    for (int i = threadIdx.x; i < PASSES * RADIX; i += THREADS) sh[i] = 0;
+    __syncthreads();
+    const u64 nvec = n >> 1;
+    const ulonglong2* kv = reinterpret_cast<const ulonglong2*>(keys);
+    const u64 stride = (u64)gridDim.x * THREADS;
+    u64 i = (u64)blockIdx.x * THREADS + threadIdx.x;
+    auto acc = [&](u64 k) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * RADIX + ((k >> (8 * p)) & 255)], 1u);
+    };
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        ulonglong2 a = __ldg(kv + i), b = __ldg(kv + i + stride), c = __ldg(kv + i + 2 * stride),
+                   d = __ldg(kv + i + 3 * stride);
+        acc(a.x); acc(a.y); acc(b.x); acc(b.y); acc(c.x); acc(c.y); acc(d.x); acc(d.y);
+    }
+    for (; i < nvec; i += stride) {
+        ulonglong2 a = __ldg(kv + i);
+        acc(a.x); acc(a.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc(keys[n - 1]);
+    __syncthreads();
+    for (int j = threadIdx.x; j < PASSES * RADIX; j += THREADS) {
+        u32 c = sh[j];
+        if (c) atomicAdd(&ghist[j], (u64)c);
+    }
+}
+
+// counts -> exclusive bases, in place; skip[p] = 1 when one bin of pass p holds every key
+__global__ void __launch_bounds__(RADIX) radix_scan_kernel(u64* __restrict__ ghist, u64 n, u32* __restrict__ skip) {
+    __shared__ u64 s[RADIX];
+    for (int p = 0; p < PASSES; ++p) {
+        u64 c = ghist[p * RADIX + threadIdx.x];
+        s[threadIdx.x] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 run = 0;
+            u32 sk = 0;
+            for (int d = 0; d < RADIX; ++d) {
+                u64 v = s[d];
+                if (v == n) sk = 1;
+                s[d] = run;
+                run += v;
+            }
+            skip[p] = sk;
+        }
+        __syncthreads();
+        ghist[p * RADIX + threadIdx.x] = s[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+template <int THREADS, int ITEMS>
+struct SweepSmem {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    static constexpr size_t bytes = (size_t)TILE * 8 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 8 + 40 * 4;
+};
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int shift,
+                const u64* __restrict__ gbase, u64* __restrict__ lookback, u32* __restrict__ tile_counter,
+                u64 epoch) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * ITEMS;
+    static_assert(THREADS >= RADIX, "one thread per digit is assumed");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* s_keys = reinterpret_cast<u64*>(smem_raw);
+    u64* s_goff = s_keys + TILE;
+    u32* s_whist = reinterpret_cast<u32*>(s_goff + RADIX);
+    u32* s_binoff = s_whist + WARPS * RADIX;
+    u32* s_scan = s_binoff + RADIX;   // 33 words + tile id
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) s_scan[34] = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) s_whist[i] = 0;
+    __syncthreads();
+    const u32 tile = s_scan[34];
+    const u64 tile_base = (u64)tile * TILE;
+    const u64 remain = n - tile_base;
+    const int valid = remain < (u64)TILE ? (int)remain : TILE;
+
+    // ---- load, warp striped ----
+    u64 key[ITEMS];
+    const u64 wbase = tile_base + (u64)warp * (ITEMS * 32) + lane;
+    if (valid == TILE) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) key[j] = ld_stream(in + wbase + j * 32);
+    } else {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u64 idx = wbase + j * 32;
+            key[j] = idx < n ? ld_stream(in + idx) : ~0ull;
+        }
+    }
+
+    // ---- rank inside the warp (stable: item order = memory order) ----
+    u32* wh = s_whist + warp * RADIX;
+    u32 rank[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) rank[j] = __match_any_sync(0xffffffffu, (u32)(key[j] >> shift) & 255u);
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const u32 d = (u32)(key[j] >> shift) & 255u;
+        const u32 peers = rank[j];
+        const u32 pre = wh[d];
+        __syncwarp();
+        const u32 below = __popc(peers & lt);
+        if (below == 0) wh[d] = pre + __popc(peers);
+        __syncwarp();
+        rank[j] = pre + below;
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive offsets across warps, tile total ----
+    u32 count = 0;
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            u32 c = s_whist[w * RADIX + tid];
+            s_whist[w * RADIX + tid] = count;
+            count += c;
+        }
+    }
+    const u32 off = block_exclusive_scan<THREADS>(tid < RADIX ? count : 0u, nullptr, s_scan);
+    if (tid < RADIX) {
+        s_binoff[tid] = off;
+        u64 vcount = count;
+        if (tid == RADIX - 1) vcount -= (u64)(TILE - valid);   // padding keys sit at the end of the last bin
+        u64* lb = lookback + (u64)tile * RADIX + tid;
+        u64 excl = 0;
+        if (tile == 0) {
+            st_volatile(lb, LB_INCL | epoch | vcount);
+        } else {
+            st_volatile(lb, LB_AGG | epoch | vcount);
+            const u64* p = lb - RADIX;
+            u32 spins = 0;
+            for (;;) {
+                u64 v = ld_volatile(p);
+                if ((v & LB_EPOCH_MASK) != epoch || (v >> 62) == 0) {            // predecessor not published yet
+                    if (++spins > (1u << 26)) __trap();                          // never hang the device on a bug
+                    continue;
+                }
+                excl += v & LB_VALUE_MASK;
+                if ((v >> 62) == 2) break;
+                p -= RADIX;
+            }
+            st_volatile(lb, LB_INCL | epoch | (excl + vcount));
+        }
+        s_goff[tid] = gbase[tid] + excl - off;
+    }
+    __syncthreads();
+
+    // ---- reorder through shared memory ----
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const u32 d = (u32)(key[j] >> shift) & 255u;
+        s_keys[s_binoff[d] + wh[d] + rank[j]] = key[j];
+    }
+    __syncthreads();
+
+    // ---- write out: consecutive threads -> consecutive addresses inside a bin ----
+    if (valid == TILE) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int i = tid + j * THREADS;
+            const u64 k = s_keys[i];
+            out[s_goff[(u32)(k >> shift) & 255u] + i] = k;
+        }
+    } else {
+        for (int i = tid; i < valid; i += THREADS) {
+            const u64 k = s_keys[i];
+            out[s_goff[(u32)(k >> shift) & 255u] + i] = k;
+        }
+    }
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
+    using S = SweepSmem<THREADS, ITEMS>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
+        attr_done = true;
+    }
+    const u64 ntiles = (n + S::TILE - 1) / S::TILE;
+    kern<<<(unsigned)ntiles, THREADS, S::bytes, st>>>(in, out, n, 8 * pass, ws.hist + pass * RADIX, ws.lookback,
+                                                        ws.tile_counter + pass, (u64)(pass + 1) << 56);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int sort_config_tile(int cfg) {
+    switch (cfg) {
+        case 1: return 512 * 16;
+        case 2: return 256 * 24;
+        case 3: return 384 * 16;
+        case 4: return 512 * 8;
+        case 5: return 1024 * 8;
+        default: return 256 * 16;
+    }
+}
+
+size_t sort_workspace_bytes(u64 n, int cfg) {
+    const u64 tile = (u64)sort_config_tile(cfg);
+    const u64 ntiles = (n + tile - 1) / tile + 1;
+    return PASSES * RADIX * 8 + 64 + ntiles * RADIX * 8;
+}
+
+int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg) {
+    ws.cfg = cfg;
+    ws.hist = reinterpret_cast<u64*>(mem);
+    ws.tile_counter = reinterpret_cast<u32*>(ws.hist + PASSES * RADIX);
+    ws.skip = ws.tile_counter + 8;
+    ws.lookback = ws.hist + PASSES * RADIX + 8;
+    const u64 tile = (u64)sort_config_tile(cfg);
+    ws.ntiles = (n + tile - 1) / tile;
+    return 0;
+}
+
+// Sorts `n` keys.  `a` holds the input; `b` is scratch of the same size.  Returns in *result which
+// of the two buffers holds the sorted keys (passes whose digit is constant are skipped).
+int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t st, u64** result) {
+    *result = a;
+    if (n <= 1) return 0;
+    CUDA_TRY(cudaMemsetAsync(ws.hist, 0, PASSES * RADIX * 8 + 64 + ws.ntiles * RADIX * 8, st));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    u64 want = (n / 2 + 511) / 512;
+    unsigned hgrid = (unsigned)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
+    radix_hist_kernel<512><<<hgrid, 512, 0, st>>>(a, n, ws.hist);
+    CUDA_TRY(cudaGetLastError());
+    radix_scan_kernel<<<1, RADIX, 0, st>>>(ws.hist, n, ws.skip);
+    DEBWT_COUNT(2);
+    CUDA_TRY(cudaGetLastError());
+    u32 skip[PASSES];
+    CUDA_TRY(cudaMemcpyAsync(skip, ws.skip, sizeof skip, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    u64 *src = a, *dst = b;
+    for (int p = 0; p < PASSES; ++p) {
+        if (skip[p]) continue;
+        int rc;
+        switch (ws.cfg) {
+            case 1: rc = launch_sweep<512, 16, 2>(src, dst, n, p, ws, st); break;
+            case 2: rc = launch_sweep<256, 24, 2>(src, dst, n, p, ws, st); break;
+            case 3: rc = launch_sweep<384, 16, 2>(src, dst, n, p, ws, st); break;
+            case 4: rc = launch_sweep<512, 8, 3>(src, dst, n, p, ws, st); break;
+            case 5: rc = launch_sweep<1024, 8, 1>(src, dst, n, p, ws, st); break;
+            default: rc = launch_sweep<256, 16, 3>(src, dst, n, p, ws, st); break;
+        }
+        if (rc) return rc;
+        DEBWT_COUNT(1);
+        u64* t = src; src = dst; dst = t;
+    }
+    *result = src;
+    return 0;
+}
+
+}  // namespace debwt

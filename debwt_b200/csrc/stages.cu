@@ -1,0 +1,725 @@
+// Device stages around the radix sort: packing, extraction, count-by-sort, branch k-mer detection,
+// branch codes, emission.  Each kernel cites the reference loop it replaces.
+#include "stages.cuh"
+
+namespace debwt {
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned grid_for(u64 work, int per_block) { return (unsigned)((work + per_block - 1) / per_block); }
+
+// =============================================================================================
+// generic exclusive scan (reduce -> scan partials -> rescan)
+// =============================================================================================
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+
+template <bool POPC>
+__device__ __forceinline__ u32 scan_f(u32 v) { return POPC ? (u32)__popc(v) : v; }
+
+template <bool POPC>
+__global__ void __launch_bounds__(TPB) scan_reduce_kernel(const u32* __restrict__ in, u64 m, u32* __restrict__ part) {
+    __shared__ u32 sm[40];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE;
+    u32 s = 0;
+#pragma unroll 4
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        u64 i = base + (u64)j * TPB + threadIdx.x;
+        if (i < m) s += scan_f<POPC>(in[i]);
+    }
+    u32 total;
+    block_exclusive_scan<TPB>(s, &total, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_partials_kernel(u32* __restrict__ part, u64 nb, u64* __restrict__ d_total) {
+    __shared__ u32 sm[40];
+    __shared__ u64 carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (u64 base = 0; base < nb; base += 1024) {
+        u64 i = base + threadIdx.x;
+        u32 v = i < nb ? part[i] : 0;
+        u32 total;
+        u32 ex = block_exclusive_scan<1024>(v, &total, sm);
+        u64 carry = carry_s;
+        if (i < nb) part[i] = (u32)(carry + ex);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && d_total) *d_total = carry_s;
+}
+
+template <bool POPC>
+__global__ void __launch_bounds__(TPB) scan_final_kernel(const u32* __restrict__ in, u32* __restrict__ out, u64 m,
+                                                        const u32* __restrict__ part) {
+    __shared__ u32 sm[40];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u32 v[SCAN_ITEMS];
+    u32 s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        u64 i = base + j;
+        v[j] = i < m ? scan_f<POPC>(in[i]) : 0;
+        s += v[j];
+    }
+    u32 ex = block_exclusive_scan<TPB>(s, nullptr, sm) + part[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        u64 i = base + j;
+        if (i < m) out[i] = ex;
+        ex += v[j];
+    }
+}
+
+}  // namespace
+
+size_t scan_workspace_bytes(u64 m) { return ((m + SCAN_TILE - 1) / SCAN_TILE + 1) * 4 + 64; }
+
+int scan_exclusive_u32(const u32* in, u32* out, u64 m, bool popc, void* workspace, u64* d_total, cudaStream_t st) {
+    if (m == 0) {
+        if (d_total) CUDA_TRY(cudaMemsetAsync(d_total, 0, 8, st));
+        return 0;
+    }
+    u32* part = reinterpret_cast<u32*>(workspace);
+    const u64 nb = (m + SCAN_TILE - 1) / SCAN_TILE;
+    if (popc) scan_reduce_kernel<true><<<(unsigned)nb, TPB, 0, st>>>(in, m, part);
+    else scan_reduce_kernel<false><<<(unsigned)nb, TPB, 0, st>>>(in, m, part);
+    scan_partials_kernel<<<1, 1024, 0, st>>>(part, nb, d_total);
+    if (popc) scan_final_kernel<true><<<(unsigned)nb, TPB, 0, st>>>(in, out, m, part);
+    else scan_final_kernel<false><<<(unsigned)nb, TPB, 0, st>>>(in, out, m, part);
+    DEBWT_COUNT(3);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// =============================================================================================
+// K1: ASCII -> 2-bit packed text            (reference src/collect#$.c:66-90)
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ u32 base_code(u32 c, u32& bad) {
+    // A/a C/c G/g T/t -> 0 1 2 3; '#' '$' (separators) are stored as T like the reference does
+    u32 u = c & 0xDFu;
+    u32 code = (u >> 1) & 3u;
+    code ^= code >> 1;
+    bool ok = (u == 0x41u) | (u == 0x43u) | (u == 0x47u) | (u == 0x54u);
+    bool sep = (c == 0x23u) | (c == 0x24u);
+    bad |= (u32)(!ok && !sep);
+    return ok ? code : 3u;
+}
+
+__global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii, u64 n, u64* __restrict__ words,
+                                                  u64 nwords, u32* __restrict__ err) {
+    const u64 w = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (w >= nwords) return;
+    const u64 base = w * 32;
+    u64 out = 0;
+    u32 bad = 0;
+    if (base + 32 <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(ascii + base);
+        uint4 a = __ldg(p), b = __ldg(p + 1);
+        u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                u32 c = (v[q] >> (8 * r)) & 255u;
+                out = (out << 2) | base_code(c, bad);
+            }
+        }
+    } else {
+        for (int j = 0; j < 32; ++j) {
+            u64 i = base + j;
+            u32 code = 3u;                          // T padding past the end (src/collect#$.c:87-90)
+            if (i < n) code = base_code(ascii[i], bad);
+            out = (out << 2) | code;
+        }
+    }
+    words[w] = out;
+    if (bad) atomicOr(err, 1u);
+}
+
+// =============================================================================================
+// K2: (k+1)-mer extraction                   (Jellyfish count, src/kmercounting.sh:8; src/mySort.c:54-83)
+// =============================================================================================
+__device__ __forceinline__ u64 record_of(const u64* __restrict__ seps, u64 n_rec, u64 p) {
+    return lower_bound_u64(seps, 0, n_rec, p);     // number of separators strictly before p
+}
+
+__global__ void __launch_bounds__(TPB) extract_kernel(const u64* __restrict__ words, u64 n,
+                                                     const u64* __restrict__ seps, u64 n_rec,
+                                                     u64* __restrict__ keys) {
+    const u64 p = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (p >= n) return;
+    const u64 r = record_of(seps, n_rec, p);
+    if (r >= n_rec) return;
+    if (p + KMER > seps[r]) return;                // window would contain the separator
+    st_stream(keys + (p - (u64)KMER * r), text_window32(words, p));
+}
+
+// =============================================================================================
+// K4: count-by-sort                           (src/mySort.c:76-77,194 kmerInfo records)
+// =============================================================================================
+constexpr int RLE_ITEMS = 8;
+constexpr int RLE_TILE = TPB * RLE_ITEMS;
+
+__global__ void __launch_bounds__(TPB) rle_count_kernel(const u64* __restrict__ k, u64 n, u32* __restrict__ tile_cnt) {
+    __shared__ u32 sm[40];
+    const u64 base = (u64)blockIdx.x * RLE_TILE + (u64)threadIdx.x * RLE_ITEMS;
+    u32 c = 0;
+#pragma unroll
+    for (int j = 0; j < RLE_ITEMS; ++j) {
+        u64 i = base + j;
+        if (i < n) c += (i == 0 || k[i] != k[i - 1]);
+    }
+    u32 total;
+    block_exclusive_scan<TPB>(c, &total, sm);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(TPB) rle_write_kernel(const u64* __restrict__ k, u64 n, const u32* __restrict__ tile_ex,
+                                                       u64* __restrict__ kmers, u64* __restrict__ starts) {
+    __shared__ u32 sm[40];
+    const u64 base = (u64)blockIdx.x * RLE_TILE + (u64)threadIdx.x * RLE_ITEMS;
+    bool h[RLE_ITEMS];
+    u32 c = 0;
+#pragma unroll
+    for (int j = 0; j < RLE_ITEMS; ++j) {
+        u64 i = base + j;
+        h[j] = i < n && (i == 0 || k[i] != k[i - 1]);
+        c += h[j];
+    }
+    u64 o = (u64)tile_ex[blockIdx.x] + block_exclusive_scan<TPB>(c, nullptr, sm);
+#pragma unroll
+    for (int j = 0; j < RLE_ITEMS; ++j)
+        if (h[j]) { kmers[o] = k[base + j]; starts[o] = base + j; ++o; }
+}
+
+}  // namespace
+
+int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st) {
+    const u64 nw = text_words(n);
+    pack_kernel<<<grid_for(nw, TPB), TPB, 0, st>>>(ascii, n, words, nw, d_err);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st) {
+    extract_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(words, n, d_seps, n_rec, keys);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(TPB) diff_kernel(const u64* __restrict__ starts, u64 d, u64 n, u64* __restrict__ counts) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i < d) counts[i] = ((i + 1 < d) ? starts[i + 1] : n) - starts[i];
+}
+}  // namespace
+
+size_t rle_workspace_bytes(u64 n) {
+    const u64 nt = (n + RLE_TILE - 1) / RLE_TILE + 1;
+    return nt * 8 + scan_workspace_bytes(nt) + n * 8 + 64;
+}
+
+int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u64* d_total, cudaStream_t st) {
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_total, 0, 8, st)); return 0; }
+    const u64 nt = (n + RLE_TILE - 1) / RLE_TILE;
+    u32* tile_cnt = reinterpret_cast<u32*>(workspace);
+    u32* tile_ex = tile_cnt + nt;
+    char* p = reinterpret_cast<char*>(tile_ex + nt);
+    p += (8 - (reinterpret_cast<uintptr_t>(p) & 7)) & 7;
+    void* scan_ws = p;
+    p += (scan_workspace_bytes(nt) + 7) & ~(size_t)7;
+    u64* starts = reinterpret_cast<u64*>(p);
+    rle_count_kernel<<<(unsigned)nt, TPB, 0, st>>>(sorted, n, tile_cnt);
+    if (scan_exclusive_u32(tile_cnt, tile_ex, nt, false, scan_ws, d_total, st)) return -1;
+    rle_write_kernel<<<(unsigned)nt, TPB, 0, st>>>(sorted, n, tile_ex, kmers, starts);
+    u64 d = 0;
+    CUDA_TRY(cudaMemcpyAsync(&d, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    diff_kernel<<<grid_for(d, TPB), TPB, 0, st>>>(starts, d, n, counts);
+    DEBWT_COUNT(3);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// =============================================================================================
+// K5/K6: in/out edges per k-mer group         (src/getKmer.c:62-120, src/INandOut.c:260-343)
+// =============================================================================================
+namespace {
+
+// first index of the group (k-mer = key >> 2) that sorted[i] belongs to
+__device__ __forceinline__ u64 group_head(const u64* __restrict__ k, u64 i) {
+    const u64 x = k[i] >> 2;
+    u64 hi = i, step = 1, lo;
+    for (;;) {
+        if (step > hi) { lo = 0; break; }
+        u64 j = hi - step;
+        if ((k[j] >> 2) == x) { hi = j; step <<= 1; }
+        else { lo = j + 1; break; }
+    }
+    return lower_bound_u64(k, lo, hi, x << 2);
+}
+
+// one past the last index of the group that sorted[i] belongs to
+__device__ __forceinline__ u64 group_end(const u64* __restrict__ k, u64 n, u64 i) {
+    const u64 x = k[i] >> 2;
+    u64 lo = i, step = 1, hi;
+    for (;;) {
+        u64 j = lo + step;
+        if (j >= n) { hi = n; break; }
+        if ((k[j] >> 2) == x) { lo = j; step <<= 1; }
+        else { hi = j; break; }
+    }
+    return upper_bound_u64(k, lo, hi, (x << 2) | 3ull);
+}
+
+__global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, u16* __restrict__ gmask) {
+    __shared__ u64 s_lo, s_hi;
+    const u64 i0 = (u64)blockIdx.x * TPB;
+    const u64 i1 = (i0 + TPB < n) ? i0 + TPB : n;
+    if (threadIdx.x == 0) {
+        const u64 a = k[i0], b = k[i1 - 1];
+        if ((a >> 62) == (b >> 62)) {
+            s_lo = lower_bound_u64(k, 0, n, a << 2);
+            s_hi = lower_bound_u64(k, 0, n, b << 2);
+        } else { s_lo = 0; s_hi = n; }
+    }
+    __syncthreads();
+    const u64 i = i0 + threadIdx.x;
+    if (i >= n) return;
+    const u64 key = k[i];
+    if (i > 0 && k[i - 1] == key) return;           // one representative per distinct (k+1)-mer
+    // out edge: k-mer = first 31 bases, next symbol = last base
+    const u64 hp = group_head(k, i);
+    atomic_or_u16(gmask, hp, 1u << (GM_OUT_SHIFT + (u32)(key & 3)));
+    // in edge: (k+1)-mer cX marks k-mer X with c
+    const u64 q = key << 2;
+    const u64 hs = lower_bound_u64(k, s_lo, s_hi, q);
+    if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << (u32)(key >> 62));
+}
+
+__global__ void __launch_bounds__(TPB) mark_heads_tails_kernel(const u64* __restrict__ words, const u64* __restrict__ seps,
+                                                              u64 n_rec, const u64* __restrict__ k, u64 n,
+                                                              u16* __restrict__ gmask) {
+    const u64 r = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (r >= n_rec) return;
+    const u64 start = r ? seps[r - 1] + 1 : 0;
+    // head k-mer: follows '#' / starts the text -> forced multi-in (src/INandOut.c:282-291)
+    u64 x = text_window32(words, start) & ~3ull;
+    u64 h = lower_bound_u64(k, 0, n, x);
+    if (h < n && (k[h] & ~3ull) == x) atomic_or_u16(gmask, h, GM_IN_SEP);
+    // tail k-mer: precedes the separator -> forced multi-out (src/INandOut.c:260-266)
+    x = text_window32(words, seps[r] - KNODE) & ~3ull;
+    h = lower_bound_u64(k, 0, n, x);
+    if (h < n && (k[h] & ~3ull) == x) atomic_or_u16(gmask, h, GM_OUT_TAIL);
+}
+
+__global__ void __launch_bounds__(TPB) propagate_kernel(const u64* __restrict__ k, u64 n, u16* __restrict__ gmask) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n || i == 0) return;
+    if ((k[i - 1] >> 2) != (k[i] >> 2)) return;     // group head keeps its own mask
+    gmask[i] = gmask[group_head(k, i)];
+}
+
+// =============================================================================================
+// K7: branch table (red/black tables of the reference, src/INandOut.c:396-417)
+// =============================================================================================
+constexpr int BR_ITEMS = 8;
+constexpr int BR_TILE = TPB * BR_ITEMS;
+
+template <bool WRITE>
+__global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, u64 n, const u16* __restrict__ gmask,
+                                                    u32* __restrict__ tile_nb, u32* __restrict__ tile_blue,
+                                                    const u32* __restrict__ tile_nb_ex, const u32* __restrict__ tile_blue_ex,
+                                                    BranchTable bt) {
+    __shared__ u32 sm[40];
+    const u64 base = (u64)blockIdx.x * BR_TILE + (u64)threadIdx.x * BR_ITEMS;
+    u32 flags[BR_ITEMS];
+    u32 size[BR_ITEMS];
+    u32 nb = 0, nblue = 0;
+#pragma unroll
+    for (int j = 0; j < BR_ITEMS; ++j) {
+        const u64 i = base + j;
+        flags[j] = 0;
+        size[j] = 0;
+        if (i < n && (i == 0 || (k[i - 1] >> 2) != (k[i] >> 2))) {
+            const u32 m = gmask[i];
+            const u32 f = (gm_multi_out(m) ? 1u : 0u) | (gm_multi_in(m) ? 2u : 0u);
+            if (f) {
+                flags[j] = f | 4u;
+                ++nb;
+                if (f & 2u) { size[j] = (u32)(group_end(k, n, i) - i); nblue += size[j]; }
+            }
+        }
+    }
+    if (!WRITE) {
+        u32 tb, tl;
+        block_exclusive_scan<TPB>(nb, &tb, sm);
+        block_exclusive_scan<TPB>(nblue, &tl, sm);
+        if (threadIdx.x == 0) { tile_nb[blockIdx.x] = tb; tile_blue[blockIdx.x] = tl; }
+    } else {
+        u64 ob = (u64)tile_nb_ex[blockIdx.x] + block_exclusive_scan<TPB>(nb, nullptr, sm);
+        u32 ol = tile_blue_ex[blockIdx.x] + block_exclusive_scan<TPB>(nblue, nullptr, sm);
+#pragma unroll
+        for (int j = 0; j < BR_ITEMS; ++j) {
+            if (flags[j]) {
+                const u64 i = base + j;
+                bt.kmer[ob] = (k[i] & ~3ull) | (flags[j] & 3u);
+                bt.head[ob] = (u32)i;
+                bt.blue[ob] = ol;
+                ol += size[j];
+                ++ob;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) branch_index_kernel(BranchTable bt) {
+    const u64 b = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (b > bt.n_branch) return;
+    const int sh = 64 - bt.bits;
+    const long long cur = (b < bt.n_branch) ? (long long)(bt.kmer[b] >> sh) : (1ll << bt.bits);
+    const long long prev = (b > 0) ? (long long)(bt.kmer[b - 1] >> sh) : -1ll;
+    for (long long t = prev + 1; t <= cur; ++t) bt.bidx[t] = (u32)b;
+}
+
+__global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict__ k, u64 n, const u64* __restrict__ pads,
+                                                         u64 m, u64* __restrict__ ins) {
+    const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (t < m) ins[t] = upper_bound_u64(k, 0, n, pads[t]);
+}
+
+}  // namespace
+
+int k_mark_edges(const u64* sorted, u64 n, u16* gmask, cudaStream_t st) {
+    if (n == 0) return 0;
+    mark_edges_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, gmask);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_mark_heads_tails(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n, u16* gmask,
+                       cudaStream_t st) {
+    mark_heads_tails_kernel<<<grid_for(n_rec, TPB), TPB, 0, st>>>(words, d_seps, n_rec, sorted, n, gmask);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_propagate(const u64* sorted, u64 n, u16* gmask, cudaStream_t st) {
+    if (n == 0) return 0;
+    propagate_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, gmask);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+namespace {
+struct BranchWs { u32 *nb, *blue, *nb_ex, *blue_ex; void* scan_ws; u64 nt; };
+BranchWs branch_ws(void* workspace, u64 n) {
+    BranchWs w;
+    w.nt = (n + BR_TILE - 1) / BR_TILE;
+    u32* p = reinterpret_cast<u32*>(workspace);
+    w.nb = p; w.blue = p + w.nt; w.nb_ex = p + 2 * w.nt; w.blue_ex = p + 3 * w.nt;
+    char* q = reinterpret_cast<char*>(p + 4 * w.nt);
+    q += (8 - (reinterpret_cast<uintptr_t>(q) & 7)) & 7;
+    w.scan_ws = q;
+    return w;
+}
+}  // namespace
+
+size_t branch_workspace_bytes(u64 n) {
+    const u64 nt = (n + BR_TILE - 1) / BR_TILE + 1;
+    return nt * 16 + 16 + scan_workspace_bytes(nt);
+}
+
+int k_branch_count(const u64* sorted, u64 n, const u16* gmask, void* workspace, u64* d_totals, cudaStream_t st) {
+    BranchWs w = branch_ws(workspace, n);
+    BranchTable none;
+    branch_kernel<false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, none);
+    DEBWT_COUNT(1);
+    if (scan_exclusive_u32(w.nb, w.nb_ex, w.nt, false, w.scan_ws, d_totals, st)) return -1;
+    if (scan_exclusive_u32(w.blue, w.blue_ex, w.nt, false, w.scan_ws, d_totals + 1, st)) return -1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st) {
+    BranchWs w = branch_ws(workspace, n);
+    branch_kernel<true><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, nullptr, nullptr, w.nb_ex, w.blue_ex, bt);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_branch_index(BranchTable bt, cudaStream_t st) {
+    branch_index_kernel<<<grid_for(bt.n_branch + 1, TPB), TPB, 0, st>>>(bt);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_special_insertion(const u64* sorted, u64 n, const u64* pads, u64 m, u64* ins, cudaStream_t st) {
+    if (m == 0) return 0;
+    special_ins_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(sorted, n, pads, m, ins);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// =============================================================================================
+// K9: branch codes and blue entries             (src/generateSP.c:534-683)
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-mer << 2, low bits 0 */, u64& b) {
+    const u64 t = x >> (64 - bt.bits);
+    u64 lo = bt.bidx[t], hi = bt.bidx[t + 1];
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        u64 v = bt.kmer[mid] & ~3ull;
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    if (lo < bt.n_branch && (bt.kmer[lo] & ~3ull) == x) { b = lo; return true; }
+    return false;
+}
+
+__global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restrict__ words, u64 n,
+                                                            const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
+                                                            u32* __restrict__ mo_bits, u64* __restrict__ blue) {
+    const u64 p = (u64)blockIdx.x * TPB + threadIdx.x;     // grid covers a multiple of 32 positions
+    bool mo = false;
+    if (p < n) {
+        const u64 r = record_of(seps, n_rec, p);
+        if (r < n_rec && p + KMER <= seps[r]) {
+            const u64 x = text_window32(words, p) & ~3ull;
+            u64 b;
+            if (branch_lookup(bt, x, b)) {
+                const u32 f = (u32)(bt.kmer[b] & 3ull);
+                mo = f & 1u;
+                if (f & 2u) {
+                    const u64 start = r ? seps[r - 1] + 1 : 0;
+                    u32 prev;
+                    if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
+                    else prev = text_symbol(words, p - 1);
+                    const u32 slot = atomicAdd(bt.cursor + b, 1u);
+                    blue[(u64)bt.blue[b] + slot] = (p << 4) | prev;
+                }
+            }
+        }
+    }
+    const u32 bal = __ballot_sync(0xffffffffu, mo);
+    if ((threadIdx.x & 31) == 0 && p < n + 32) mo_bits[p >> 5] = bal;
+}
+
+__global__ void __launch_bounds__(TPB) patch_bits_kernel(u32* __restrict__ mo_bits, const u64* __restrict__ pos, u64 m) {
+    const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (t < m) atomicOr(mo_bits + (pos[t] >> 5), 1u << (pos[t] & 31));
+}
+
+__global__ void __launch_bounds__(TPB) emit_codes_kernel(const u64* __restrict__ words, u64 nbw,
+                                                        const u32* __restrict__ mo_bits, const u32* __restrict__ word_prefix,
+                                                        u64* __restrict__ sp_codes) {
+    const u64 w = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (w >= nbw) return;
+    u32 bits = mo_bits[w];
+    if (!bits) return;
+    // next symbols of positions 32w+b are text positions 32w+31+b: last symbol of word w, then word w+1
+    const u64 w0 = words[w], w1 = words[w + 1];
+    u64 c = word_prefix[w];
+    u64 acc = 0, acc_word = c >> 5;
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const u64 code = (b == 0) ? (w0 & 3ull) : ((w1 >> (2 * (32 - b))) & 3ull);
+        const u64 cw = c >> 5;
+        if (cw != acc_word) {
+            if (acc) atomicOr(sp_codes + acc_word, acc);
+            acc = 0; acc_word = cw;
+        }
+        acc |= code << (2 * (31 - (c & 31)));
+        ++c;
+    }
+    if (acc) atomicOr(sp_codes + acc_word, acc);
+}
+
+__device__ __forceinline__ u64 sp_index_of(const u32* __restrict__ mo_bits, const u32* __restrict__ word_prefix, u64 p) {
+    const u32 bits = mo_bits[p >> 5];
+    return (u64)word_prefix[p >> 5] + __popc(bits & ((1u << (p & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(TPB) mark_sep_codes_kernel(const u32* __restrict__ mo_bits, const u32* __restrict__ word_prefix,
+                                                            const u64* __restrict__ pos, u64 m, u32* __restrict__ sp_sep,
+                                                            u64* __restrict__ out_idx) {
+    const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (t >= m) return;
+    const u64 c = sp_index_of(mo_bits, word_prefix, pos[t]);
+    atomicOr(sp_sep + (c >> 5), 1u << (c & 31));
+    out_idx[t] = c;
+}
+
+__global__ void __launch_bounds__(TPB) blue_fix_kernel(u64* __restrict__ blue, u64 m, const u32* __restrict__ mo_bits,
+                                                      const u32* __restrict__ word_prefix) {
+    const u64 e = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (e >= m) return;
+    const u64 v = blue[e];
+    blue[e] = (sp_index_of(mo_bits, word_prefix, v >> 4) << 4) | (v & 15ull);
+}
+
+}  // namespace
+
+int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, u32* mo_bits, u64* blue,
+                     cudaStream_t st) {
+    const u64 npos = (n + 31) & ~31ull;
+    flag_positions_kernel<<<grid_for(npos, TPB), TPB, 0, st>>>(words, n, d_seps, n_rec, bt, mo_bits, blue);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_patch_bits(u32* mo_bits, const u64* positions, u64 m, cudaStream_t st) {
+    if (m == 0) return 0;
+    patch_bits_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(mo_bits, positions, m);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_emit_codes(const u64* words, u64 n, const u32* mo_bits, const u32* word_prefix, u64* sp_codes, cudaStream_t st) {
+    const u64 nbw = (n + 31) / 32;
+    emit_codes_kernel<<<grid_for(nbw, TPB), TPB, 0, st>>>(words, nbw, mo_bits, word_prefix, sp_codes);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_mark_sep_codes(const u32* mo_bits, const u32* word_prefix, const u64* positions, u64 m, u32* sp_sep,
+                     u64* d_code_index_out, cudaStream_t st) {
+    if (m == 0) return 0;
+    mark_sep_codes_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(mo_bits, word_prefix, positions, m, sp_sep, d_code_index_out);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_blue_fix(u64* blue, u64 m, const u32* mo_bits, const u32* word_prefix, cudaStream_t st) {
+    if (m == 0) return 0;
+    blue_fix_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(blue, m, mo_bits, word_prefix);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// =============================================================================================
+// K8 / K11: emission                             (src/INandOut.c:367-395, src/insertCase3.c:56-104)
+// =============================================================================================
+namespace {
+
+constexpr int FILL_WORDS_PER_WARP = 8;
+
+__global__ void __launch_bounds__(TPB) fill_case2_kernel(const u16* __restrict__ gmask, u64 n_keys, u64 n,
+                                                        const u64* __restrict__ spec_rows, u64 m, u64 nwords,
+                                                        u64* __restrict__ bwt) {
+    __shared__ u64 s_lo, s_hi;
+    constexpr int WORDS_PER_BLOCK = (TPB / 32) * FILL_WORDS_PER_WARP;
+    const u64 wblock = (u64)blockIdx.x * WORDS_PER_BLOCK;
+    if (threadIdx.x == 0) {
+        s_lo = lower_bound_u64(spec_rows, 0, m, wblock * 32);
+        s_hi = lower_bound_u64(spec_rows, 0, m, (wblock + WORDS_PER_BLOCK) * 32);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 lo = s_lo, hi = s_hi;
+#pragma unroll
+    for (int q = 0; q < FILL_WORDS_PER_WARP; ++q) {
+        const u64 w = wblock + (u64)warp * FILL_WORDS_PER_WARP + q;
+        if (w >= nwords) break;                       // warp-uniform
+        const u64 row = w * 32 + lane;
+        u32 code = 0;
+        if (row < n) {
+            const u64 t = lower_bound_u64(spec_rows, lo, hi, row);   // special rows before this row
+            const bool special = t < m && spec_rows[t] == row;
+            const u64 i = row - t;
+            if (!special && i < n_keys) {
+                const u32 mk = gmask[i];
+                if (!gm_multi_in(mk) && (mk & 15u)) code = (u32)__ffs(mk & 15u) - 1u;   // the single in-base (src/INandOut.c:367-395)
+            }
+        }
+        const u32 hi32 = __reduce_or_sync(0xffffffffu, lane < 16 ? code << (2 * (15 - lane)) : 0u);
+        const u32 lo32 = __reduce_or_sync(0xffffffffu, lane >= 16 ? code << (2 * (31 - lane)) : 0u);
+        if (lane == 0) bwt[w] = ((u64)hi32 << 32) | lo32;
+    }
+}
+
+__device__ __forceinline__ void bwt_or(u64* __restrict__ bwt, u64 row, u32 code) {
+    atomicOr(bwt + (row >> 5), (u64)code << (2 * (31 - (row & 31))));
+}
+
+__global__ void __launch_bounds__(TPB) emit_blue_kernel(const u64* __restrict__ blue, BranchTable bt,
+                                                       const u64* __restrict__ spec_ins, u64 m, u64* __restrict__ bwt,
+                                                       u64* __restrict__ sharp_rows, u32* __restrict__ sharp_count,
+                                                       u64* __restrict__ dollar_row) {
+    const u64 e = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (e >= bt.n_blue) return;
+    // segment = last branch entry whose blue offset is <= e
+    u64 lo = 0, hi = bt.n_branch;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if ((u64)bt.blue[mid] <= e) lo = mid + 1; else hi = mid;
+    }
+    const u64 b = lo - 1;
+    const u64 i = (u64)bt.head[b] + (e - bt.blue[b]);
+    const u64 row = i + upper_bound_u64(spec_ins, 0, m, i);
+    const u32 c = (u32)(blue[e] & 15ull);
+    if (c >= 4) {
+        if (c == 4) sharp_rows[atomicAdd(sharp_count, 1u)] = row; else *dollar_row = row;
+        bwt_or(bwt, row, 3u);                                   // '#'/'$' stored as T (src/insertCase3.c:84-95)
+    } else if (c) {
+        bwt_or(bwt, row, c);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) emit_special_kernel(const u64* __restrict__ rows, const u8* __restrict__ chr, u64 m,
+                                                          u64* __restrict__ bwt) {
+    const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (t < m && chr[t]) bwt_or(bwt, rows[t], chr[t]);
+}
+
+}  // namespace
+
+int k_fill_case2(const u16* gmask, u64 n_keys, u64 n, const u64* spec_rows, u64 m, u64* bwt, cudaStream_t st) {
+    const u64 nwords = (n + 31) / 32;
+    constexpr int WORDS_PER_BLOCK = (TPB / 32) * FILL_WORDS_PER_WARP;
+    fill_case2_kernel<<<grid_for(nwords, WORDS_PER_BLOCK), TPB, 0, st>>>(gmask, n_keys, n, spec_rows, m, nwords, bwt);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_emit_blue(const u64* blue, BranchTable bt, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
+                u32* d_sharp_count, u64* dollar_row, cudaStream_t st) {
+    if (bt.n_blue == 0) return 0;
+    emit_blue_kernel<<<grid_for(bt.n_blue, TPB), TPB, 0, st>>>(blue, bt, spec_ins, m, bwt, sharp_rows, d_sharp_count,
+                                                               dollar_row);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_emit_special(const u64* spec_rows, const u8* spec_chr, u64 m, u64* bwt, cudaStream_t st) {
+    if (m == 0) return 0;
+    emit_special_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(spec_rows, spec_chr, m, bwt);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace debwt

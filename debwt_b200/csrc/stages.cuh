@@ -1,0 +1,80 @@
+// Device stages of the deBWT-B200 pipeline other than the radix sort.
+#pragma once
+#include "common.cuh"
+
+namespace debwt {
+
+// ---- generic exclusive scan of u32 values (optionally popcounts of the input words) -----------
+size_t scan_workspace_bytes(u64 m);
+// out[i] = sum_{j<i} f(in[j]), f = identity or popc; *d_total (device u64) = sum of all
+int scan_exclusive_u32(const u32* in, u32* out, u64 m, bool popc, void* workspace, u64* d_total, cudaStream_t st);
+
+// ---- K1 / K2 ------------------------------------------------------------------------------
+// ascii: n bytes (bases, '#' between records, '$' last).  words: ceil((n+32)/32)+1 u64.
+int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st);
+inline u64 text_words(u64 n) { return (n + 32 + 31) / 32 + 1; }
+// all in-record 32-mers; key index of window p in record r is p - 32 r.  keys: n - 32 R entries.
+int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st);
+
+// ---- K4 count-by-sort (API parity with the reference's kmerInfo records) -------------------
+// returns D through *d_total; kmers/counts sized >= n
+int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u64* d_total, cudaStream_t st);
+size_t rle_workspace_bytes(u64 n);
+
+// ---- K5..K7 branch k-mer detection ---------------------------------------------------------
+int k_mark_edges(const u64* sorted, u64 n, u16* gmask, cudaStream_t st);
+int k_mark_heads_tails(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n, u16* gmask,
+                       cudaStream_t st);
+int k_propagate(const u64* sorted, u64 n, u16* gmask, cudaStream_t st);
+
+struct BranchTable {
+    u64 n_branch = 0;      // B
+    u64 n_blue = 0;        // M
+    u64* kmer = nullptr;   // [B]  (k-mer << 2) | multi_in << 1 | multi_out, ascending
+    u32* head = nullptr;   // [B]  index of the group's first sorted key
+    u32* blue = nullptr;   // [B+1] exclusive prefix of blue-segment sizes (0 for non multi-in)
+    u32* cursor = nullptr; // [B]  fill cursor per segment
+    u32* bidx = nullptr;   // [2^bits + 1] direct index on the top `bits` bits of the k-mer
+    int bits = 0;
+};
+size_t branch_workspace_bytes(u64 n);
+// pass 1: counts (B, M) -> d_totals[0], d_totals[1]
+int k_branch_count(const u64* sorted, u64 n, const u16* gmask, void* workspace, u64* d_totals, cudaStream_t st);
+// pass 2: fills kmer/head/blue (arrays must be allocated from the counts)
+int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st);
+int k_branch_index(BranchTable bt, cudaStream_t st);
+
+// ---- sentinel-window ("special") suffixes --------------------------------------------------
+// ins[t] = upper_bound(sorted, pad[t]) for t < m
+int k_special_insertion(const u64* sorted, u64 n, const u64* pads, u64 m, u64* ins, cudaStream_t st);
+
+// ---- K9 branch codes + blue entries --------------------------------------------------------
+// mo_bits: ceil(n/32)+1 u32 words; blue: M u64 entries (position << 4 | prev)
+int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, u32* mo_bits, u64* blue,
+                     cudaStream_t st);
+int k_patch_bits(u32* mo_bits, const u64* positions, u64 m, cudaStream_t st);
+// sp_codes: ceil(S/32)+3 u64 zeroed; codes packed 32 per word, code j at bits 2*(31-(j&31))
+int k_emit_codes(const u64* words, u64 n, const u32* mo_bits, const u32* word_prefix, u64* sp_codes, cudaStream_t st);
+// marks separator codes: sp_sep bit per code (u32 words, zeroed); positions = tail positions whose code is '#'/'$'
+int k_mark_sep_codes(const u32* mo_bits, const u32* word_prefix, const u64* positions, u64 m, u32* sp_sep,
+                     u64* d_code_index_out, cudaStream_t st);
+int k_blue_fix(u64* blue, u64 m, const u32* mo_bits, const u32* word_prefix, cudaStream_t st);
+
+// ---- K10 segmented sort (bluesort.cu) ------------------------------------------------------
+struct SpView {
+    const u64* codes;   // 2-bit codes
+    const u32* sep;     // 1 bit per code: code is '#' or '$'
+    u64 dollar_index;   // index of the one '$' code
+    u64 n_codes;        // S
+};
+int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work /* >= B+4 u32 */, cudaStream_t st);
+
+// ---- K8 / K11 emission ---------------------------------------------------------------------
+// bwt: ceil(n/32) words.  spec_rows: m ascending rows of the special suffixes.
+int k_fill_case2(const u16* gmask, u64 n_keys, u64 n, const u64* spec_rows, u64 m, u64* bwt, cudaStream_t st);
+// scatter sorted blue symbols; '#'/'$' rows appended to sharp_rows (unordered) / dollar_row
+int k_emit_blue(const u64* blue, BranchTable bt, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
+                u32* d_sharp_count, u64* dollar_row, cudaStream_t st);
+int k_emit_special(const u64* spec_rows, const u8* spec_chr, u64 m, u64* bwt, cudaStream_t st);
+
+}  // namespace debwt

@@ -1,0 +1,112 @@
+/*
+ * deBWT-B200 -- C ABI of the B200-native BWT-construction hot path.
+ *
+ * This is the drop-in boundary for the reference's stage functions (reference src/main.h:1-8,
+ * sequenced by src/main.c:83-149).  The reference has no FFI; its "interface" is a linear pipeline of
+ * C functions communicating through process-wide globals and temp files.  Each entry point below
+ * names the reference interface it replaces.  Plain pointers and sizes only -- no CUDA, torch or C++
+ * types -- so it binds from C (host/debwt_main.c), ctypes (debwt_b200/binding.py), cgo, JNI, ...
+ *
+ * Conventions: every function returns 0 on success and a negative value on error; the message is
+ * available from debwt_last_error().  A context is bound to one CUDA device; calls on one context
+ * are synchronous and not thread-safe (the reference's stages are not re-entrant either).  The
+ * library owns all device memory.  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef DEBWT_B200_H
+#define DEBWT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct debwt_ctx debwt_ctx;
+
+/* Per-phase device times (CUDA events on the library's stream) and sizes of the last build.
+   Replaces the per-stage clock()/time() printfs of src/main.c:86-170. */
+typedef struct debwt_stats {
+    uint64_t n_symbols;      /* N = sum(len) + n_records            (BWTLEN, src/collect#$.c:56-57) */
+    uint64_t n_records;
+    uint64_t n_keys;         /* in-record 32-mer windows n' = N - 32 R */
+    uint64_t n_branch;       /* branch k-mers (red table size)      (src/INandOut.c:396-417) */
+    uint64_t n_blue;         /* occurrences of multi-in k-mers      (blueTable size) */
+    uint64_t n_codes;        /* branch-code (SP) length S           (src/generateSP.c) */
+    uint64_t n_special;      /* sentinel-window suffixes, 32 R */
+    float ms_h2d;            /* host -> device copy of the ASCII text */
+    float ms_pack;           /* K1 */
+    float ms_extract;        /* K2 */
+    float ms_sort;           /* K3: the named roofline phase (histogram + 8 scatter passes) */
+    float ms_classify;       /* K5-K7 */
+    float ms_special;        /* sentinel-window suffix handling (device + host) */
+    float ms_codes;          /* K9 */
+    float ms_bluesort;       /* K10 */
+    float ms_emit;           /* K8 + K11 */
+    float ms_d2h;            /* device -> host copy of the result */
+    float ms_total;          /* whole debwt_build() */
+    uint32_t sort_launches;  /* kernel launches inside the sort phase */
+    uint32_t total_launches; /* kernel launches inside debwt_build() */
+} debwt_stats;
+
+const char* debwt_last_error(void);
+/* number of CUDA devices visible (0 when the driver is missing) */
+int debwt_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Replaces the process-wide globals of the reference (src/collect#$.h:17-18,31, generateSP.h:1-6,
+   sortBlue.h:1-5, insertCase3.h:1-4).  `device` is the CUDA ordinal. */
+int debwt_create(debwt_ctx** out, int device);
+void debwt_destroy(debwt_ctx* ctx);
+/* tuning knob for the sort kernel configuration (0 = default); returns the previous value */
+int debwt_set_sort_config(debwt_ctx* ctx, int cfg);
+
+/* ---- input: replaces collect()'s FASTA pass, src/collect#$.c:27-90 ---------------------------- */
+/* Host records: `seqs[i]` points at `lens[i]` bases (ACGT, either case; no terminator needed).
+   Every record must be longer than 32 bp (src/collect#$.c:41-45) and contain only ACGT.
+   The text T = S1 # S2 # ... Sn $ is assembled on the device (H2D copy happens here). */
+int debwt_set_records(debwt_ctx* ctx, const char* const* seqs, const uint64_t* lens, uint64_t n_records);
+/* Same, from one host buffer that already holds T as ASCII ('#' between records, '$' last).
+   `seps[i]` = offset of the i-th separator (ascending; the last one is n_symbols-1). */
+int debwt_set_text(debwt_ctx* ctx, const char* text, uint64_t n_symbols, const uint64_t* seps, uint64_t n_records);
+/* Same layout, but `d_text` is a DEVICE pointer on the context's device (no host copy); the buffer
+   is only read, and must stay valid until debwt_build() returns. */
+int debwt_set_text_device(debwt_ctx* ctx, const void* d_text, uint64_t n_symbols, const uint64_t* seps,
+                          uint64_t n_records);
+
+/* ---- build: replaces mySort .. insertCase3, src/main.c:83-149 -------------------------------- */
+/* `k` is the CLI -k value (12..32).  The output does not depend on it; the
+   device path always uses 32-base keys.  The result stays on the device until copied out. */
+int debwt_build(debwt_ctx* ctx, int k);
+
+/* ---- output: replaces insertCase3's three fwrite()s, src/insertCase3.c:115-131 ------------- */
+int debwt_result_sizes(const debwt_ctx* ctx, uint64_t* n_symbols, uint64_t* n_words, uint64_t* n_sharp);
+/* bwt_words: ceil(N/32) u64, symbol j at bits 2*(31-(j&31)) of word j>>5, '#'/'$' stored as T;
+   sharp_rows: n_records-1 ascending rows holding '#'; dollar_row: the row holding '$'. */
+int debwt_result_copy(debwt_ctx* ctx, uint64_t* bwt_words, uint64_t* sharp_rows, uint64_t* dollar_row);
+int debwt_get_stats(const debwt_ctx* ctx, debwt_stats* out);
+
+/* ---- per-kernel entry points (host buffers in, host buffers out) for parity tests -------------- */
+/* K1: ASCII text -> 2-bit packed words, ceil((n+32)/32) of them (src/collect#$.c:78-90). */
+int debwt_k_pack(int device, const char* text, uint64_t n_symbols, uint64_t* words_out);
+/* K2: all in-record 32-mers as left-aligned keys in text order; keys_out holds n - 32 R entries
+   (Jellyfish count semantics, src/kmercounting.sh:8; packing of src/mySort.c:61-75). */
+int debwt_k_extract(int device, const char* text, uint64_t n_symbols, const uint64_t* seps, uint64_t n_records,
+                    uint64_t* keys_out);
+/* K3: ascending sort of 64-bit keys in place (src/mySort.c:98-176).  *ms_out (optional) = device time. */
+int debwt_k_radix_sort_u64(int device, uint64_t* keys, uint64_t n, int cfg, float* ms_out);
+/* K4: count-by-sort of sorted keys -> {kmer, count} (kmerInfo, src/mySort.c:76-77,194); returns D. */
+int debwt_k_rle(int device, const uint64_t* sorted, uint64_t n, uint64_t* kmers_out, uint64_t* counts_out,
+                uint64_t* n_distinct_out);
+/* K5-K7: per sorted key the in/out mask of its k-mer group (src/INandOut.c:253-343):
+   bits 0-3 in-bases, bit 4 '#'/'$' predecessor, bits 8-11 out-bases, bit 12 precedes a separator. */
+int debwt_k_group_masks(int device, const char* text, uint64_t n_symbols, const uint64_t* seps, uint64_t n_records,
+                        uint16_t* masks_out /* n - 32 R */);
+
+/* Device-resident sort benchmark helper: sorts `n` pseudo-random keys `iters` times on the device
+   (keys regenerated on device before each run) and returns the mean device ms per sort. */
+int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEBWT_B200_H */
