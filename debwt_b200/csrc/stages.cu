@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii,
     } else {
         for (int j = 0; j < 32; ++j) {
             u64 i = base + j;
-            u32 code = 3u;                          // T padding past the end (src/collect#$.c:87-90)
+            u32 code = (i < n + 32) ? 3u : 0u;      // exactly 32 T of padding past the end (src/collect#$.c:87-90)
             if (i < n) code = base_code(ascii[i], bad);
             out = (out << 2) | code;
         }
