@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- BWT build throughput (Mbp/s) of the deBWT hot path on B200, next to the CPU reference.
+
+Contract (one JSON line on stdout, printed by rank 0):
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+  N > 1 is launched by the driver through torch.distributed.run (one rank per GPU).
+
+A "step" is one pass of the whole hot path (2-bit pack -> 32-mer extraction -> LSD radix sort ->
+branch k-mer detection -> branch codes -> segmented sort -> BWT emission) over one synthetic genome.
+  value : input bases / device time, text already resident in HBM (CUDA events on the library's stream)
+  e2e   : same metric through the public C-ABI call sequence with HOST buffers: pinned host text ->
+          H2D -> build -> D2H of the packed BWT, every step
+  roofline : the dominant kernel (onesweep_kernel, the radix-sort scatter pass): 16 B/key algorithmic
+          per launch / mean launch time, against the measured HBM copy bandwidth
+  cpu_baseline : the compiled reference (oracle/_ref/deBWT + Jellyfish stand-in) on a bounded sample
+--impl reference times the reference's own CPU implementation on the same workload (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bwt_build_throughput"
+UNIT = "Mbp/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# ------------------------------------------------------------------------------------------------
+def make_workload(name: str, rank: int = 0):
+    from debwt_b200 import synth
+    if name == "c1":
+        return synth.config1(), "synthetic 4.6 Mbp random ACGT single sequence, k=32"
+    if name == "c2":
+        return synth.config2(), "synthetic 100 Mbp sequence with planted repeats (5% copies of 10 kbp elements), k=32"
+    if name == "c2s":
+        return synth.config2(20_000_000), "synthetic 20 Mbp sequence with planted repeats (reduced C2, smoke only)"
+    if name == "c4s":
+        return synth.config4(10_000_000, 10), "10 synthetic 10 Mbp genomes at 0.1% divergence (reduced C4)"
+    if name == "c3s":
+        return synth.config3(400_000_000, 4), "synthetic 400 Mbp genome with repeat families (reduced C3)"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def sample_records(records, max_bases: int):
+    """Bounded prefix of the workload for the CPU arms."""
+    out, left = [], max_bases
+    for r in records:
+        if left <= 33:
+            break
+        out.append(r[:left])
+        left -= out[-1].size
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per onesweep launch from the committed ncu summary (profiles/), scaled per key."""
+    p = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p))
+        except ValueError:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------
+def run_reference_sample(records, max_bases: int, threads: int):
+    from debwt_b200 import synth
+    from oracle import refrun
+    if not refrun.available():
+        raise RuntimeError("oracle/_ref is not built")
+    sample = sample_records(records, max_bases)
+    nb = int(sum(r.size for r in sample))
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "sample.fa")
+        synth.write_fasta(sample, fa)
+        res = refrun.run_reference(fa, threads=threads, timeout=3600, scratch_root=d)
+    return nb, res
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation (oracle/_ref/deBWT, all host threads) on a bounded sample
+    of the same workload, sized so that steps + warmup runs end within a few minutes."""
+    if rank != 0:
+        return
+    records, desc = make_workload(args.workload)
+    cores = os.cpu_count() or 1
+    total = int(sum(r.size for r in records))
+    runs = max(args.steps + args.warmup, 1)
+    per_run_s = 170.0 / runs                                  # whole arm within ~3 minutes
+    sample = int(min(total, max(2_000_000, (per_run_s - 3.0) * 1.0e6)))   # ~1 Mbp/s + ~3 s fixed cost per run
+    if args.ref_sample:
+        sample = min(total, args.ref_sample)
+    times, standin = [], []
+    nb = sample
+    for i in range(runs):
+        nb, res = run_reference_sample(records, sample, cores)
+        if i >= args.warmup:
+            times.append(res.wall_s); standin.append(res.standin_s)
+    t = sum(times) / len(times)
+    v = nb / t / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "sample": f"first {nb} bases of the workload per step"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"oracle/_ref/deBWT -t {cores} -k 32 on the first {nb} bases; Jellyfish replaced by "
+                                       f"oracle/jellyfish_standin.c ({sum(standin) / len(standin):.2f} s of the {t:.2f} s per step)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    from debwt_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    records, desc = make_workload(args.workload, rank)
+    text_np, seps = api.join_records(records)
+    n = int(text_np.size)
+    n_bases = n - len(records)
+    # pinned host staging + device-resident copy
+    h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_text.numpy()[:] = text_np
+    d_text = h_text.to("cuda", non_blocking=False)
+    n_words = (n + 31) // 32
+    h_out = torch.empty(n_words, dtype=torch.int64, pin_memory=True)
+
+    b = api.BwtBuilder(device=local_rank)
+
+    def step_resident():
+        b.set_text_device(d_text.data_ptr(), n, seps)
+        b.build()
+        return b.stats()
+
+    def step_e2e():
+        b.set_text_ptr(h_text.data_ptr(), n, seps)
+        b.build()
+        b.result_into(h_out.data_ptr())
+        return b.stats()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        dev_ms, sort_ms, sweep_ms, launches, sweeps, last = 0.0, 0.0, 0.0, 0, 0, None
+        for _ in range(args.steps):
+            st = step_resident()
+            dev_ms += st["ms_total"]; sort_ms += st["ms_sort"]; sweep_ms += st["ms_sort_sweeps"]
+            launches += st["total_launches"]; sweeps += st["sort_sweeps"]
+            last = st
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = clk.summary()
+    ms_dev = dev_ms / args.steps
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    if dist is not None:
+        tt = torch.tensor([ms_dev, e2e_ms, wall_ms / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, e2e_ms, wall_step = (float(x) for x in tt.tolist())
+    else:
+        wall_step = wall_ms / args.steps
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nk = last["n_keys"]
+        per_launch_ms = sweep_ms / max(sweeps, 1)
+        achieved = 16.0 * nk / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        phase = 136.0 * nk / ((sort_ms / args.steps) * 1e-3) / 1e9 if sort_ms > 0 else 0.0
+        traffic = ncu_traffic_per_launch()
+        line = {
+            "metric": METRIC, "value": world * n_bases / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "n_bases": n_bases, "n_records": len(records), "k": 32,
+                       "l2": "inputs larger than L2 (text %d MB, keys %d MB per step)" % (n // 2**20, 8 * nk // 2**20),
+                       "parallelism": "replicas" if world > 1 else "single GPU",
+                       "timing": "CUDA events on the library stream (debwt_stats.ms_total); wall per step %.3f ms" % wall_step},
+            "clocks": clocks,
+            "e2e": {"value": world * n_bases / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": n,
+                    "d2h_bytes_per_step": 8 * n_words + 8 * len(records), "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (radix-sort scatter pass, %d launches/step)" % (sweeps // args.steps),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": 16 * nk,
+                         "mean_launch_ms": per_launch_ms,
+                         "traffic": (traffic or {}).get("dram_bytes_per_key", None) and traffic["dram_bytes_per_key"] * nk,
+                         "sort_phase": {"achieved": phase, "frac": phase / peak, "bytes_per_key": 136,
+                                        "ms": sort_ms / args.steps}},
+            "phases_ms": {k: last[k] for k in last if k.startswith("ms_")},
+            "sizes": {k: last[k] for k in ("n_symbols", "n_keys", "n_branch", "n_blue", "n_codes", "n_special")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cores = os.cpu_count() or 1
+                nb, res = run_reference_sample(records, args.cpu_sample, cores)
+                line["cpu_baseline"] = {"value": nb / res.wall_s / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"oracle/_ref/deBWT -t {cores} -k 32 on the first {nb} bases of the workload: "
+                                                  f"{res.wall_s:.2f} s wall of which {res.standin_s:.2f} s in the Jellyfish stand-in "
+                                                  f"(deBWT proper {nb / max(res.proper_s, 1e-9) / 1e6:.2f} Mbp/s)"}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    b.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--cpu-sample", type=int, default=12_000_000, help="bases of the workload the cpu_baseline leg runs")
+    ap.add_argument("--ref-sample", type=int, default=0, help="bases per step of the --impl reference arm (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,9 +24,9 @@ class DebwtError(RuntimeError):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, c_u64) for n in ("n_symbols", "n_records", "n_keys", "n_branch", "n_blue", "n_codes", "n_special")] + \
-               [(n, ctypes.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_classify", "ms_special",
+               [(n, ctypes.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_sort_sweeps", "ms_classify", "ms_special",
                                               "ms_codes", "ms_bluesort", "ms_emit", "ms_d2h", "ms_total")] + \
-               [("sort_launches", ctypes.c_uint32), ("total_launches", ctypes.c_uint32)]
+               [("sort_launches", ctypes.c_uint32), ("sort_sweeps", ctypes.c_uint32), ("total_launches", ctypes.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

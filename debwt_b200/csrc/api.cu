@@ -71,7 +71,7 @@ using namespace debwt;
 
 struct debwt_ctx {
     int device = 0;
-    int sort_cfg = 0;
+    int sort_cfg = 1;   // 512 threads x 16 keys per tile (fastest measured on B200, profiles/)
     cudaStream_t st = nullptr;
     DevPool pool;
     // input
@@ -326,10 +326,13 @@ int debwt_build(debwt_ctx* c, int k) {
     if (pool.alloc(&d_sortws, sort_workspace_bytes(nk, c->sort_cfg))) return -1;
     SortWorkspace ws;
     sort_workspace_bind(ws, d_sortws, nk, c->sort_cfg);
+    int sweeps = 0;
+    ws.ev_sweep_begin = c->ev[11]; ws.ev_sweep_end = c->ev[12]; ws.sweeps_out = &sweeps;
     const unsigned launches_before_sort = g_launches;
     u64* d_keys = nullptr;
     if (radix_sort_u64(d_ka, d_kb, nk, ws, st, &d_keys)) return -1;
     S.sort_launches = g_launches - launches_before_sort;
+    S.sort_sweeps = (u32)sweeps;
     pool.release(d_sortws);
     pool.release(d_keys == d_ka ? d_kb : d_ka);
     u32 h_err = 0;
@@ -503,6 +506,7 @@ int debwt_build(debwt_ctx* c, int k) {
     float* ms[] = {&S.ms_pack, &S.ms_extract, &S.ms_sort, &S.ms_classify, &S.ms_special, &S.ms_codes, &S.ms_bluesort, &S.ms_emit};
     for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventElapsedTime(ms[i], c->ev[i], c->ev[i + 1]));
     CUDA_TRY(cudaEventElapsedTime(&S.ms_total, c->ev[0], c->ev[8]));
+    if (S.sort_sweeps) CUDA_TRY(cudaEventElapsedTime(&S.ms_sort_sweeps, c->ev[11], c->ev[12]));
     S.total_launches = g_launches;
     c->built = true;
     return 0;

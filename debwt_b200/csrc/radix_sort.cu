@@ -89,7 +89,7 @@ struct SweepSmem {
     static constexpr size_t bytes = (size_t)TILE * 8 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 8 + 40 * 4;
 };
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH_BALLOT>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int shift,
                 const u64* __restrict__ gbase, u64* __restrict__ lookback, u32* __restrict__ tile_counter,
@@ -131,7 +131,22 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int sh
     u32* wh = s_whist + warp * RADIX;
     u32 rank[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) rank[j] = __match_any_sync(0xffffffffu, (u32)(key[j] >> shift) & 255u);
+    for (int j = 0; j < ITEMS; ++j) {
+        const u32 d = (u32)(key[j] >> shift) & 255u;
+        if (MATCH_BALLOT) {
+            // warp-ballot ranking: one vote per digit bit leaves the mask of lanes holding the same digit
+            u32 peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const u32 vote = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? vote : ~vote;
+            }
+            rank[j] = peers;
+        } else {
+            rank[j] = __match_any_sync(0xffffffffu, d);
+        }
+    }
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
@@ -209,10 +224,10 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int sh
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH_BALLOT = true>
 int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
     using S = SweepSmem<THREADS, ITEMS>;
-    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, MATCH_BALLOT>;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
@@ -234,6 +249,8 @@ int sort_config_tile(int cfg) {
         case 3: return 384 * 16;
         case 4: return 512 * 8;
         case 5: return 1024 * 8;
+        case 7: return 256 * 12;
+        case 8: return 256 * 8;
         default: return 256 * 16;
     }
 }
@@ -275,6 +292,8 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
     CUDA_TRY(cudaMemcpyAsync(skip, ws.skip, sizeof skip, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     u64 *src = a, *dst = b;
+    int sweeps = 0;
+    if (ws.ev_sweep_begin) CUDA_TRY(cudaEventRecord(ws.ev_sweep_begin, st));
     for (int p = 0; p < PASSES; ++p) {
         if (skip[p]) continue;
         int rc;
@@ -284,12 +303,18 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
             case 3: rc = launch_sweep<384, 16, 2>(src, dst, n, p, ws, st); break;
             case 4: rc = launch_sweep<512, 8, 3>(src, dst, n, p, ws, st); break;
             case 5: rc = launch_sweep<1024, 8, 1>(src, dst, n, p, ws, st); break;
+            case 6: rc = launch_sweep<256, 16, 3, false>(src, dst, n, p, ws, st); break;
+            case 7: rc = launch_sweep<256, 12, 4>(src, dst, n, p, ws, st); break;
+            case 8: rc = launch_sweep<256, 8, 5>(src, dst, n, p, ws, st); break;
             default: rc = launch_sweep<256, 16, 3>(src, dst, n, p, ws, st); break;
         }
         if (rc) return rc;
         DEBWT_COUNT(1);
+        ++sweeps;
         u64* t = src; src = dst; dst = t;
     }
+    if (ws.ev_sweep_end) CUDA_TRY(cudaEventRecord(ws.ev_sweep_end, st));
+    if (ws.sweeps_out) *ws.sweeps_out = sweeps;
     *result = src;
     return 0;
 }

@@ -11,6 +11,8 @@ struct SortWorkspace {
     u32* skip = nullptr;          // [8] pass has a constant digit
     u64* lookback = nullptr;      // [ntiles][256] decoupled look-back words
     u64 ntiles = 0;
+    cudaEvent_t ev_sweep_begin = nullptr, ev_sweep_end = nullptr;   // optional: bracket the scatter passes
+    int* sweeps_out = nullptr;                                        // optional: number of passes launched
 };
 
 int sort_config_tile(int cfg);

@@ -37,6 +37,7 @@ typedef struct debwt_stats {
     float ms_pack;           /* K1 */
     float ms_extract;        /* K2 */
     float ms_sort;           /* K3: the named roofline phase (histogram + 8 scatter passes) */
+    float ms_sort_sweeps;    /* K3: the scatter passes alone (onesweep_kernel launches) */
     float ms_classify;       /* K5-K7 */
     float ms_special;        /* sentinel-window suffix handling (device + host) */
     float ms_codes;          /* K9 */
@@ -45,6 +46,7 @@ typedef struct debwt_stats {
     float ms_d2h;            /* device -> host copy of the result */
     float ms_total;          /* whole debwt_build() */
     uint32_t sort_launches;  /* kernel launches inside the sort phase */
+    uint32_t sort_sweeps;    /* onesweep_kernel launches (8 unless a digit is constant) */
     uint32_t total_launches; /* kernel launches inside debwt_build() */
 } debwt_stats;
 

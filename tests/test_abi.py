@@ -18,8 +18,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_stats_struct_matches_header_layout():
-    # 7 u64 + 11 float + 2 u32 = 56 + 44 + 8 = 108 -> padded to 112
-    assert ctypes.sizeof(binding.Stats) == 112
+    # 7 u64 + 12 float + 3 u32 = 56 + 48 + 12 = 116 -> padded to 120
+    assert ctypes.sizeof(binding.Stats) == 120
 
 
 def test_no_cpu_fallback_without_device():
