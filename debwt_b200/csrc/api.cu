@@ -343,8 +343,12 @@ int debwt_build(debwt_ctx* c, int k) {
     u16* d_gmask = nullptr;
     if (dalloc(pool, &d_gmask, nk + 2)) return -1;
     CUDA_TRY(cudaMemsetAsync(d_gmask, 0, (nk + 2) * 2, st));
-    if (k_mark_edges(d_keys, nk, d_gmask, st)) return -1;
-    if (k_mark_heads_tails(d_text, d_seps, R, d_keys, nk, d_gmask, st)) return -1;
+    KeyIndex ki;
+    ki.bits = key_index_bits(nk);
+    if (dalloc(pool, &ki.idx, (1ull << ki.bits) + 2)) return -1;
+    if (k_build_key_index(d_keys, nk, ki, st)) return -1;
+    if (k_mark_edges(d_keys, nk, ki, d_gmask, st)) return -1;
+    if (k_mark_heads_tails(d_text, d_seps, R, d_keys, nk, ki, d_gmask, st)) return -1;
     if (k_propagate(d_keys, nk, d_gmask, st)) return -1;
     void* d_brws = nullptr; u64* d_tot = nullptr;
     if (pool.alloc(&d_brws, branch_workspace_bytes(nk)) || dalloc(pool, &d_tot, 4)) return -1;
@@ -397,7 +401,7 @@ int debwt_build(debwt_ctx* c, int k) {
     u64 *d_pads = nullptr, *d_ins = nullptr;
     if (dalloc(pool, &d_pads, nspec) || dalloc(pool, &d_ins, nspec)) return -1;
     CUDA_TRY(cudaMemcpyAsync(d_pads, h_pads.data(), nspec * 8, cudaMemcpyHostToDevice, st));
-    if (k_special_insertion(d_keys, nk, d_pads, nspec, d_ins, st)) return -1;
+    if (k_special_insertion(d_keys, nk, ki, d_pads, nspec, d_ins, st)) return -1;
     CUDA_TRY(cudaMemcpyAsync(h_ins.data(), d_ins, nspec * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<u64> h_rows(nspec);
@@ -500,7 +504,7 @@ int debwt_build(debwt_ctx* c, int k) {
     for (void* p : {(void*)d_seps, (void*)d_text, (void*)d_err, (void*)d_keys, (void*)d_gmask, (void*)d_tot,
                     (void*)bt.kmer, (void*)bt.head, (void*)bt.blue, (void*)bt.cursor, (void*)bt.bidx, (void*)d_pads,
                     (void*)d_ins, (void*)d_rows, (void*)d_chr, (void*)d_emit, (void*)d_tail, (void*)d_tail_idx,
-                    (void*)d_mo, (void*)d_wp, (void*)d_blue, d_scanws, (void*)d_codes, (void*)d_sep, (void*)d_work})
+                    (void*)d_mo, (void*)d_wp, (void*)d_blue, d_scanws, (void*)d_codes, (void*)d_sep, (void*)d_work, (void*)ki.idx})
         pool.release(p);
 
     float* ms[] = {&S.ms_pack, &S.ms_extract, &S.ms_sort, &S.ms_classify, &S.ms_special, &S.ms_codes, &S.ms_bluesort, &S.ms_emit};
@@ -661,8 +665,10 @@ int debwt_k_group_masks(int device, const char* text, uint64_t n, const uint64_t
     if (open_scratch(s, device)) return -1;
     const u64 nk = n - 32 * R;
     u8* d_a; u64 *d_w, *d_s, *d_ka, *d_kb; u32* d_e; u16* d_g; void* d_ws;
+    KeyIndex ki;
+    ki.bits = key_index_bits(nk);
     if (s.get(&d_a, n + 64) || s.get(&d_w, text_words(n)) || s.get(&d_e, 4) || s.get(&d_s, R) || s.get(&d_ka, nk + 2) ||
-        s.get(&d_kb, nk + 2) || s.get(&d_g, nk + 2))
+        s.get(&d_kb, nk + 2) || s.get(&d_g, nk + 2) || s.get(&ki.idx, (1ull << ki.bits) + 2))
         return -1;
     CUDA_TRY(cudaMalloc(&d_ws, sort_workspace_bytes(nk, 0)));
     s.ptrs.push_back(d_ws);
@@ -674,8 +680,9 @@ int debwt_k_group_masks(int device, const char* text, uint64_t n, const uint64_t
     CUDA_TRY(cudaMemsetAsync(d_g, 0, (nk + 2) * 2, s.st));
     u64* d_keys = nullptr;
     if (k_pack(d_a, n, d_w, d_e, s.st) || k_extract(d_w, n, d_s, R, d_ka, s.st) ||
-        radix_sort_u64(d_ka, d_kb, nk, ws, s.st, &d_keys) || k_mark_edges(d_keys, nk, d_g, s.st) ||
-        k_mark_heads_tails(d_w, d_s, R, d_keys, nk, d_g, s.st) || k_propagate(d_keys, nk, d_g, s.st))
+        radix_sort_u64(d_ka, d_kb, nk, ws, s.st, &d_keys) || k_build_key_index(d_keys, nk, ki, s.st) ||
+        k_mark_edges(d_keys, nk, ki, d_g, s.st) || k_mark_heads_tails(d_w, d_s, R, d_keys, nk, ki, d_g, s.st) ||
+        k_propagate(d_keys, nk, d_g, s.st))
         return -1;
     CUDA_TRY(cudaMemcpyAsync(masks_out, d_g, nk * 2, cudaMemcpyDeviceToHost, s.st));
     CUDA_TRY(cudaStreamSynchronize(s.st));

@@ -7,12 +7,15 @@
 //   * one histogram sweep builds all eight 256-bin digit histograms in shared memory (8 B/key read);
 //   * eight "onesweep" passes, each reading every key once and writing it once (16 B/key):
 //       - a tile of THREADS*ITEMS keys is loaded warp-striped (coalesced 256 B per warp load);
-//       - keys are ranked inside the warp with match.any (warp-ballot ranking) against a per-warp
-//         shared-memory digit histogram;
+//       - keys are ranked inside the warp by warp-ballot matching (8 votes per key, one per digit bit)
+//         against a per-warp shared-memory digit histogram;
 //       - per-digit tile totals are chained across tiles by decoupled look-back (one 64-bit word
-//         carries status + epoch + value, so no fences and no reset between passes);
-//       - the tile is reordered in shared memory and written out bin by bin, so every warp store
-//         covers contiguous addresses.
+//         carries status + epoch + value, so no fences and no reset between passes); the look-back
+//         runs after the tile has been reordered in shared memory, so its latency is hidden;
+//       - the tile is written out bin by bin, so every warp store covers contiguous addresses.
+//   B200 has ~2.4x the HBM bandwidth of H100 with about the same SM count, so the pass is
+//   instruction-issue bound unless the per-key instruction count is kept near 2: the digit position
+//   is a template parameter, the ballot sequence is hand-written, destinations are 32-bit indices.
 //   Algorithmic traffic: 8 + 8*16 = 136 B/key.
 #include "radix_sort.cuh"
 
@@ -38,8 +41,15 @@ __global__ void __launch_bounds__(THREADS) radix_hist_kernel(const u64* __restri
     const u64 stride = (u64)gridDim.x * THREADS;
     u64 i = (u64)blockIdx.x * THREADS + threadIdx.x;
     auto acc = [&](u64 k) {
-#pragma unroll
-        for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * RADIX + ((k >> (8 * p)) & 255)], 1u);
+        const u32 lo = (u32)k, hi = (u32)(k >> 32);
+        atomicAdd(&sh[0 * RADIX + (lo & 255u)], 1u);
+        atomicAdd(&sh[1 * RADIX + ((lo >> 8) & 255u)], 1u);
+        atomicAdd(&sh[2 * RADIX + ((lo >> 16) & 255u)], 1u);
+        atomicAdd(&sh[3 * RADIX + (lo >> 24)], 1u);
+        atomicAdd(&sh[4 * RADIX + (hi & 255u)], 1u);
+        atomicAdd(&sh[5 * RADIX + ((hi >> 8) & 255u)], 1u);
+        atomicAdd(&sh[6 * RADIX + ((hi >> 16) & 255u)], 1u);
+        atomicAdd(&sh[7 * RADIX + (hi >> 24)], 1u);
     };
     for (; i + 3 * stride < nvec; i += 4 * stride) {
         ulonglong2 a = __ldg(kv + i), b = __ldg(kv + i + stride), c = __ldg(kv + i + 2 * stride),
@@ -86,71 +96,81 @@ template <int THREADS, int ITEMS>
 struct SweepSmem {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int TILE = THREADS * ITEMS;
-    static constexpr size_t bytes = (size_t)TILE * 8 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 8 + 40 * 4;
+    static constexpr size_t bytes = (size_t)TILE * 8 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 4 + 40 * 4;
 };
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH_BALLOT>
+template <int PASS>
+__device__ __forceinline__ u32 digit_of(u64 key) {
+    const u32 w = PASS < 4 ? (u32)key : (u32)(key >> 32);
+    constexpr int s = 8 * (PASS & 3);
+    return s == 24 ? (w >> 24) : ((w >> s) & 255u);
+}
+
+// lanes of the warp that hold the same 8-bit digit: one ballot per digit bit
+__device__ __forceinline__ u32 match_digit(u32 d) {
+    u32 peers;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 v, t;\n\t"
+        "and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; mov.b32 %0, v;\n\t"
+        "and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
+        "}"
+        : "=&r"(peers)
+        : "r"(d));
+    return peers;
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int shift,
-                const u64* __restrict__ gbase, u64* __restrict__ lookback, u32* __restrict__ tile_counter,
-                u64 epoch) {
+onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, const u64* __restrict__ gbase,
+                u64* __restrict__ lookback, u32* __restrict__ tile_counter, u64 epoch) {
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * ITEMS;
     static_assert(THREADS >= RADIX, "one thread per digit is assumed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* s_keys = reinterpret_cast<u64*>(smem_raw);
-    u64* s_goff = s_keys + TILE;
-    u32* s_whist = reinterpret_cast<u32*>(s_goff + RADIX);
+    u32* s_whist = reinterpret_cast<u32*>(s_keys + TILE);
     u32* s_binoff = s_whist + WARPS * RADIX;
-    u32* s_scan = s_binoff + RADIX;   // 33 words + tile id
+    u32* s_goff = s_binoff + RADIX;
+    u32* s_scan = s_goff + RADIX;   // 33 words + tile id
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) s_scan[34] = atomicAdd(tile_counter, 1u);
     for (int i = tid; i < WARPS * RADIX; i += THREADS) s_whist[i] = 0;
     __syncthreads();
     const u32 tile = s_scan[34];
-    const u64 tile_base = (u64)tile * TILE;
-    const u64 remain = n - tile_base;
-    const int valid = remain < (u64)TILE ? (int)remain : TILE;
+    const u32 tile_base = tile * (u32)TILE;
+    const u32 remain = n - tile_base;
+    const int valid = remain < (u32)TILE ? (int)remain : TILE;
 
     // ---- load, warp striped ----
     u64 key[ITEMS];
-    const u64 wbase = tile_base + (u64)warp * (ITEMS * 32) + lane;
+    const u64* src = in + tile_base + warp * (ITEMS * 32) + lane;
     if (valid == TILE) {
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) key[j] = ld_stream(in + wbase + j * 32);
+        for (int j = 0; j < ITEMS; ++j) key[j] = ld_stream(src + j * 32);
     } else {
+        const u32 first = tile_base + warp * (ITEMS * 32) + lane;
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            u64 idx = wbase + j * 32;
-            key[j] = idx < n ? ld_stream(in + idx) : ~0ull;
-        }
+        for (int j = 0; j < ITEMS; ++j) key[j] = (first + j * 32 < n) ? ld_stream(src + j * 32) : ~0ull;
     }
 
     // ---- rank inside the warp (stable: item order = memory order) ----
     u32* wh = s_whist + warp * RADIX;
     u32 rank[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const u32 d = (u32)(key[j] >> shift) & 255u;
-        if (MATCH_BALLOT) {
-            // warp-ballot ranking: one vote per digit bit leaves the mask of lanes holding the same digit
-            u32 peers = 0xffffffffu;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const u32 vote = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? vote : ~vote;
-            }
-            rank[j] = peers;
-        } else {
-            rank[j] = __match_any_sync(0xffffffffu, d);
-        }
-    }
+    for (int j = 0; j < ITEMS; ++j) rank[j] = match_digit(digit_of<PASS>(key[j]));
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        const u32 d = (u32)(key[j] >> shift) & 255u;
+        const u32 d = digit_of<PASS>(key[j]);
         const u32 peers = rank[j];
         const u32 pre = wh[d];
         __syncwarp();
@@ -172,20 +192,31 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int sh
         }
     }
     const u32 off = block_exclusive_scan<THREADS>(tid < RADIX ? count : 0u, nullptr, s_scan);
+    u64 vcount = count;
+    u64* lb = lookback + (u64)tile * RADIX + tid;
     if (tid < RADIX) {
         s_binoff[tid] = off;
-        u64 vcount = count;
         if (tid == RADIX - 1) vcount -= (u64)(TILE - valid);   // padding keys sit at the end of the last bin
-        u64* lb = lookback + (u64)tile * RADIX + tid;
+        // publish this tile's count right away; the prefix is resolved after the shared-memory reorder
+        st_volatile(lb, (tile == 0 ? LB_INCL : LB_AGG) | epoch | vcount);
+    }
+    __syncthreads();
+
+    // ---- reorder through shared memory ----
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const u32 d = digit_of<PASS>(key[j]);
+        s_keys[s_binoff[d] + wh[d] + rank[j]] = key[j];
+    }
+
+    // ---- decoupled look-back (one thread per digit) ----
+    if (tid < RADIX) {
         u64 excl = 0;
-        if (tile == 0) {
-            st_volatile(lb, LB_INCL | epoch | vcount);
-        } else {
-            st_volatile(lb, LB_AGG | epoch | vcount);
+        if (tile != 0) {
             const u64* p = lb - RADIX;
             u32 spins = 0;
             for (;;) {
-                u64 v = ld_volatile(p);
+                const u64 v = ld_volatile(p);
                 if ((v & LB_EPOCH_MASK) != epoch || (v >> 62) == 0) {            // predecessor not published yet
                     if (++spins > (1u << 26)) __trap();                          // never hang the device on a bug
                     continue;
@@ -196,15 +227,7 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int sh
             }
             st_volatile(lb, LB_INCL | epoch | (excl + vcount));
         }
-        s_goff[tid] = gbase[tid] + excl - off;
-    }
-    __syncthreads();
-
-    // ---- reorder through shared memory ----
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const u32 d = (u32)(key[j] >> shift) & 255u;
-        s_keys[s_binoff[d] + wh[d] + rank[j]] = key[j];
+        s_goff[tid] = (u32)(gbase[tid] + excl) - off;
     }
     __syncthreads();
 
@@ -212,32 +235,46 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int sh
     if (valid == TILE) {
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            const int i = tid + j * THREADS;
+            const u32 i = tid + j * THREADS;
             const u64 k = s_keys[i];
-            out[s_goff[(u32)(k >> shift) & 255u] + i] = k;
+            out[s_goff[digit_of<PASS>(k)] + i] = k;
         }
     } else {
-        for (int i = tid; i < valid; i += THREADS) {
+        for (u32 i = tid; i < (u32)valid; i += THREADS) {
             const u64 k = s_keys[i];
-            out[s_goff[(u32)(k >> shift) & 255u] + i] = k;
+            out[s_goff[digit_of<PASS>(k)] + i] = k;
         }
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool MATCH_BALLOT = true>
-int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS>
+int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, cudaStream_t st) {
     using S = SweepSmem<THREADS, ITEMS>;
-    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, MATCH_BALLOT>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS>;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_done = true;
     }
     const u64 ntiles = (n + S::TILE - 1) / S::TILE;
-    kern<<<(unsigned)ntiles, THREADS, S::bytes, st>>>(in, out, n, 8 * pass, ws.hist + pass * RADIX, ws.lookback,
-                                                        ws.tile_counter + pass, (u64)(pass + 1) << 56);
+    kern<<<(unsigned)ntiles, THREADS, S::bytes, st>>>(in, out, (u32)n, ws.hist + PASS * RADIX, ws.lookback,
+                                                        ws.tile_counter + PASS, (u64)(PASS + 1) << 56);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
+    switch (pass) {
+        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0>(in, out, n, ws, st);
+        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1>(in, out, n, ws, st);
+        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2>(in, out, n, ws, st);
+        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3>(in, out, n, ws, st);
+        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4>(in, out, n, ws, st);
+        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5>(in, out, n, ws, st);
+        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6>(in, out, n, ws, st);
+        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7>(in, out, n, ws, st);
+    }
 }
 
 }  // namespace
@@ -247,10 +284,8 @@ int sort_config_tile(int cfg) {
         case 1: return 512 * 16;
         case 2: return 256 * 24;
         case 3: return 384 * 16;
-        case 4: return 512 * 8;
+        case 4: return 512 * 12;
         case 5: return 1024 * 8;
-        case 7: return 256 * 12;
-        case 8: return 256 * 8;
         default: return 256 * 16;
     }
 }
@@ -272,11 +307,16 @@ int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg) {
     return 0;
 }
 
-// Sorts `n` keys.  `a` holds the input; `b` is scratch of the same size.  Returns in *result which
-// of the two buffers holds the sorted keys (passes whose digit is constant are skipped).
+// Sorts `n` keys (n < 2^32 per call: one device's share).  `a` holds the input; `b` is scratch of the
+// same size.  Returns in *result which of the two buffers holds the sorted keys (passes whose digit
+// is constant are skipped).
 int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t st, u64** result) {
     *result = a;
     if (n <= 1) return 0;
+    if (n >= (1ull << 32) - (1u << 16)) {
+        set_error("radix_sort_u64: at most 2^32 - 65536 keys per device call");
+        return -1;
+    }
     CUDA_TRY(cudaMemsetAsync(ws.hist, 0, PASSES * RADIX * 8 + 64 + ws.ntiles * RADIX * 8, st));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -301,11 +341,8 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
             case 1: rc = launch_sweep<512, 16, 2>(src, dst, n, p, ws, st); break;
             case 2: rc = launch_sweep<256, 24, 2>(src, dst, n, p, ws, st); break;
             case 3: rc = launch_sweep<384, 16, 2>(src, dst, n, p, ws, st); break;
-            case 4: rc = launch_sweep<512, 8, 3>(src, dst, n, p, ws, st); break;
+            case 4: rc = launch_sweep<512, 12, 2>(src, dst, n, p, ws, st); break;
             case 5: rc = launch_sweep<1024, 8, 1>(src, dst, n, p, ws, st); break;
-            case 6: rc = launch_sweep<256, 16, 3, false>(src, dst, n, p, ws, st); break;
-            case 7: rc = launch_sweep<256, 12, 4>(src, dst, n, p, ws, st); break;
-            case 8: rc = launch_sweep<256, 8, 5>(src, dst, n, p, ws, st); break;
             default: rc = launch_sweep<256, 16, 3>(src, dst, n, p, ws, st); break;
         }
         if (rc) return rc;

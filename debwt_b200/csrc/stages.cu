@@ -280,44 +280,43 @@ __device__ __forceinline__ u64 group_end(const u64* __restrict__ k, u64 n, u64 i
     return upper_bound_u64(k, lo, hi, (x << 2) | 3ull);
 }
 
-__global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, u16* __restrict__ gmask) {
-    __shared__ u64 s_lo, s_hi;
-    const u64 i0 = (u64)blockIdx.x * TPB;
-    const u64 i1 = (i0 + TPB < n) ? i0 + TPB : n;
-    if (threadIdx.x == 0) {
-        const u64 a = k[i0], b = k[i1 - 1];
-        if ((a >> 62) == (b >> 62)) {
-            s_lo = lower_bound_u64(k, 0, n, a << 2);
-            s_hi = lower_bound_u64(k, 0, n, b << 2);
-        } else { s_lo = 0; s_hi = n; }
-    }
-    __syncthreads();
-    const u64 i = i0 + threadIdx.x;
+__global__ void __launch_bounds__(TPB) key_index_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i > n) return;
+    const int sh = 64 - ki.bits;
+    const long long cur = (i < n) ? (long long)(k[i] >> sh) : (1ll << ki.bits);
+    const long long prev = (i > 0) ? (long long)(k[i - 1] >> sh) : -1ll;
+    for (long long t = prev + 1; t <= cur; ++t) ki.idx[t] = (u32)i;
+}
+
+__global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     const u64 key = k[i];
     if (i > 0 && k[i - 1] == key) return;           // one representative per distinct (k+1)-mer
     // out edge: k-mer = first 31 bases, next symbol = last base
     const u64 hp = group_head(k, i);
     atomic_or_u16(gmask, hp, 1u << (GM_OUT_SHIFT + (u32)(key & 3)));
-    // in edge: (k+1)-mer cX marks k-mer X with c
+    // in edge: (k+1)-mer cX marks k-mer X with c.  Consecutive threads query ascending X (same c), so the
+    // index lookups and the short searches behind them stream through memory.
     const u64 q = key << 2;
-    const u64 hs = lower_bound_u64(k, s_lo, s_hi, q);
+    const u64 hs = indexed_lower_bound(k, ki, q);
     if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << (u32)(key >> 62));
 }
 
 __global__ void __launch_bounds__(TPB) mark_heads_tails_kernel(const u64* __restrict__ words, const u64* __restrict__ seps,
-                                                              u64 n_rec, const u64* __restrict__ k, u64 n,
+                                                              u64 n_rec, const u64* __restrict__ k, u64 n, KeyIndex ki,
                                                               u16* __restrict__ gmask) {
     const u64 r = (u64)blockIdx.x * TPB + threadIdx.x;
     if (r >= n_rec) return;
     const u64 start = r ? seps[r - 1] + 1 : 0;
     // head k-mer: follows '#' / starts the text -> forced multi-in (src/INandOut.c:282-291)
     u64 x = text_window32(words, start) & ~3ull;
-    u64 h = lower_bound_u64(k, 0, n, x);
+    u64 h = indexed_lower_bound(k, ki, x);
     if (h < n && (k[h] & ~3ull) == x) atomic_or_u16(gmask, h, GM_IN_SEP);
     // tail k-mer: precedes the separator -> forced multi-out (src/INandOut.c:260-266)
     x = text_window32(words, seps[r] - KNODE) & ~3ull;
-    h = lower_bound_u64(k, 0, n, x);
+    h = indexed_lower_bound(k, ki, x);
     if (h < n && (k[h] & ~3ull) == x) atomic_or_u16(gmask, h, GM_OUT_TAIL);
 }
 
@@ -390,25 +389,32 @@ __global__ void __launch_bounds__(TPB) branch_index_kernel(BranchTable bt) {
     for (long long t = prev + 1; t <= cur; ++t) bt.bidx[t] = (u32)b;
 }
 
-__global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict__ k, u64 n, const u64* __restrict__ pads,
-                                                         u64 m, u64* __restrict__ ins) {
+__global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki,
+                                                         const u64* __restrict__ pads, u64 m, u64* __restrict__ ins) {
     const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (t < m) ins[t] = upper_bound_u64(k, 0, n, pads[t]);
+    if (t < m) ins[t] = indexed_upper_bound(k, ki, pads[t]);
 }
 
 }  // namespace
 
-int k_mark_edges(const u64* sorted, u64 n, u16* gmask, cudaStream_t st) {
-    if (n == 0) return 0;
-    mark_edges_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, gmask);
+int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
+    key_index_kernel<<<grid_for(n + 1, TPB), TPB, 0, st>>>(sorted, n, ki);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int k_mark_heads_tails(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n, u16* gmask,
+int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t st) {
+    if (n == 0) return 0;
+    mark_edges_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, ki, gmask);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_mark_heads_tails(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n, KeyIndex ki, u16* gmask,
                        cudaStream_t st) {
-    mark_heads_tails_kernel<<<grid_for(n_rec, TPB), TPB, 0, st>>>(words, d_seps, n_rec, sorted, n, gmask);
+    mark_heads_tails_kernel<<<grid_for(n_rec, TPB), TPB, 0, st>>>(words, d_seps, n_rec, sorted, n, ki, gmask);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -467,9 +473,9 @@ int k_branch_index(BranchTable bt, cudaStream_t st) {
     return 0;
 }
 
-int k_special_insertion(const u64* sorted, u64 n, const u64* pads, u64 m, u64* ins, cudaStream_t st) {
+int k_special_insertion(const u64* sorted, u64 n, KeyIndex ki, const u64* pads, u64 m, u64* ins, cudaStream_t st) {
     if (m == 0) return 0;
-    special_ins_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(sorted, n, pads, m, ins);
+    special_ins_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(sorted, n, ki, pads, m, ins);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

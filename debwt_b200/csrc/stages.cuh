@@ -21,9 +21,29 @@ int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, 
 int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u64* d_total, cudaStream_t st);
 size_t rle_workspace_bytes(u64 n);
 
+// ---- direct index over the sorted keys (the reference's 4^12 bucket table, src/mySort.c:98-103) ----
+struct KeyIndex {
+    u32* idx = nullptr;   // [2^bits + 1]: idx[t] = first sorted position whose top `bits` bits are >= t
+    int bits = 0;
+};
+inline int key_index_bits(u64 n) {
+    int b = 8;
+    while (b < 26 && (8ull << b) < n) ++b;      // about 8 keys per bucket
+    return b;
+}
+int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st);
+__host__ __device__ __forceinline__ u64 indexed_lower_bound(const u64* __restrict__ k, const KeyIndex& ki, u64 q) {
+    const u64 t = q >> (64 - ki.bits);
+    return lower_bound_u64(k, ki.idx[t], ki.idx[t + 1], q);
+}
+__host__ __device__ __forceinline__ u64 indexed_upper_bound(const u64* __restrict__ k, const KeyIndex& ki, u64 q) {
+    const u64 t = q >> (64 - ki.bits);
+    return upper_bound_u64(k, ki.idx[t], ki.idx[t + 1], q);
+}
+
 // ---- K5..K7 branch k-mer detection ---------------------------------------------------------
-int k_mark_edges(const u64* sorted, u64 n, u16* gmask, cudaStream_t st);
-int k_mark_heads_tails(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n, u16* gmask,
+int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t st);
+int k_mark_heads_tails(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n, KeyIndex ki, u16* gmask,
                        cudaStream_t st);
 int k_propagate(const u64* sorted, u64 n, u16* gmask, cudaStream_t st);
 
@@ -46,7 +66,7 @@ int k_branch_index(BranchTable bt, cudaStream_t st);
 
 // ---- sentinel-window ("special") suffixes --------------------------------------------------
 // ins[t] = upper_bound(sorted, pad[t]) for t < m
-int k_special_insertion(const u64* sorted, u64 n, const u64* pads, u64 m, u64* ins, cudaStream_t st);
+int k_special_insertion(const u64* sorted, u64 n, KeyIndex ki, const u64* pads, u64 m, u64* ins, cudaStream_t st);
 
 // ---- K9 branch codes + blue entries --------------------------------------------------------
 // mo_bits: ceil(n/32)+1 u32 words; blue: M u64 entries (position << 4 | prev)
