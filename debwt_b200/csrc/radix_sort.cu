@@ -96,7 +96,8 @@ template <int THREADS, int ITEMS>
 struct SweepSmem {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int TILE = THREADS * ITEMS;
-    static constexpr size_t bytes = (size_t)TILE * 8 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 4 + 40 * 4;
+    static constexpr size_t bytes = (size_t)TILE * 8 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 4 + 40 * 4 +
+                                    (size_t)(THREADS / RADIX) * RADIX * 4;
 };
 
 template <int PASS>
@@ -140,6 +141,7 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, const 
     u32* s_binoff = s_whist + WARPS * RADIX;
     u32* s_goff = s_binoff + RADIX;
     u32* s_scan = s_goff + RADIX;   // 33 words + tile id
+    u32* s_part = s_scan + 40;      // [GROUPS][RADIX] partial digit totals
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) s_scan[34] = atomicAdd(tile_counter, 1u);
@@ -162,33 +164,49 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, const 
         for (int j = 0; j < ITEMS; ++j) key[j] = (first + j * 32 < n) ? ld_stream(src + j * 32) : ~0ull;
     }
 
-    // ---- rank inside the warp (stable: item order = memory order) ----
+    // ---- rank inside the warp (stable: item order = memory order); two 16-bit ranks per register ----
     u32* wh = s_whist + warp * RADIX;
-    u32 rank[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) rank[j] = match_digit(digit_of<PASS>(key[j]));
+    u32 rank2[(ITEMS + 1) / 2];
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const u32 d = digit_of<PASS>(key[j]);
-        const u32 peers = rank[j];
+        const u32 peers = match_digit(d);
         const u32 pre = wh[d];
         __syncwarp();
         const u32 below = __popc(peers & lt);
         if (below == 0) wh[d] = pre + __popc(peers);
         __syncwarp();
-        rank[j] = pre + below;
+        const u32 r = pre + below;
+        if (j & 1) rank2[j >> 1] |= r << 16; else rank2[j >> 1] = r;
     }
     __syncthreads();
 
-    // ---- per digit: exclusive offsets across warps, tile total ----
-    u32 count = 0;
-    if (tid < RADIX) {
+    // ---- per digit: exclusive offsets across warps (GROUPS thread groups share the warps), tile total ----
+    constexpr int GROUPS = THREADS / RADIX;               // 256 -> 1, 384 -> 1, 512 -> 2, 1024 -> 4
+    constexpr int WPG = WARPS / GROUPS;                   // warps per group
+    static_assert(WPG * GROUPS == WARPS, "warps must divide evenly over the digit groups");
+    const int dg = tid & (RADIX - 1), grp = tid >> 8;
+    u32 part = 0;
+    if (grp < GROUPS) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            u32 c = s_whist[w * RADIX + tid];
-            s_whist[w * RADIX + tid] = count;
-            count += c;
+        for (int w = 0; w < WPG; ++w) {
+            u32* q = s_whist + (grp * WPG + w) * RADIX + dg;
+            const u32 c = *q;
+            *q = part;
+            part += c;
+        }
+        if (GROUPS > 1) s_part[grp * RADIX + dg] = part;
+    }
+    u32 count = part, before = 0;
+    if (GROUPS > 1) {
+        __syncthreads();
+        count = 0;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+            const u32 v = s_part[g * RADIX + dg];
+            if (g < grp) before += v;
+            count += v;
         }
     }
     const u32 off = block_exclusive_scan<THREADS>(tid < RADIX ? count : 0u, nullptr, s_scan);
@@ -201,33 +219,55 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, const 
         st_volatile(lb, (tile == 0 ? LB_INCL : LB_AGG) | epoch | vcount);
     }
     __syncthreads();
+    // fold the bin offset into the per-warp offsets: one shared-memory lookup per key in the reorder
+    if (grp < GROUPS) {
+        const u32 base = s_binoff[dg] + before;
+#pragma unroll
+        for (int w = 0; w < WPG; ++w) s_whist[(grp * WPG + w) * RADIX + dg] += base;
+    }
+    __syncthreads();
 
     // ---- reorder through shared memory ----
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const u32 d = digit_of<PASS>(key[j]);
-        s_keys[s_binoff[d] + wh[d] + rank[j]] = key[j];
+        const u32 r = (j & 1) ? (rank2[j >> 1] >> 16) : (rank2[j >> 1] & 0xffffu);
+        s_keys[wh[d] + r] = key[j];
     }
 
     // ---- decoupled look-back (one thread per digit) ----
     if (tid < RADIX) {
         u64 excl = 0;
         if (tile != 0) {
-            const u64* p = lb - RADIX;
+            // walk the predecessors LB_BATCH at a time: the loads of one batch are independent, so a long
+            // run of count-only predecessors costs one memory round trip per batch instead of per tile
+            constexpr int LB_BATCH = 4;
+            u32 left = tile;                       // predecessors not yet consumed
+            const u64* p = lb - RADIX;             // nearest unconsumed predecessor
             u32 spins = 0;
-            for (;;) {
-                const u64 v = ld_volatile(p);
-                if ((v & LB_EPOCH_MASK) != epoch || (v >> 62) == 0) {            // predecessor not published yet
-                    if (++spins > (1u << 26)) __trap();                          // never hang the device on a bug
-                    continue;
+            bool done = false;
+            while (!done) {
+                u64 v[LB_BATCH];
+#pragma unroll
+                for (int i = 0; i < LB_BATCH; ++i) v[i] = ((u32)i < left) ? ld_volatile(p - (size_t)i * RADIX) : 0;
+                int used = 0;
+#pragma unroll
+                for (int i = 0; i < LB_BATCH; ++i) {
+                    if (done || used != i) continue;                       // stop at the first unpublished entry
+                    if ((u32)i >= left) continue;
+                    const u64 x = v[i];
+                    if ((x & LB_EPOCH_MASK) != epoch || (x >> 62) == 0) continue;
+                    excl += x & LB_VALUE_MASK;
+                    used = i + 1;
+                    if ((x >> 62) == 2) done = true;
                 }
-                excl += v & LB_VALUE_MASK;
-                if ((v >> 62) == 2) break;
-                p -= RADIX;
+                p -= (size_t)used * RADIX;
+                left -= used;
+                if (used == 0 && ++spins > (1u << 24)) __trap();           // never hang the device on a bug
             }
             st_volatile(lb, LB_INCL | epoch | (excl + vcount));
         }
-        s_goff[tid] = (u32)(gbase[tid] + excl) - off;
+        s_goff[tid] = (u32)(gbase[tid] + excl) - s_binoff[tid];
     }
     __syncthreads();
 
