@@ -17,6 +17,7 @@
 #include "../../include/debwt_b200.h"
 #include "radix_sort.cuh"
 #include "stages.cuh"
+#include "special.cuh"
 
 namespace debwt {
 
@@ -61,9 +62,12 @@ struct Special {
     u32 j;        // bases before the separator (0..31)
     u32 rec;
     u64 ins, row;
-    u8 chr;
+    u64 w0, w1;   // 32 symbols at the position / right after its separator
+    u8 chr, next;
     bool emit;
 };
+
+constexpr u64 kMaxDeviceSpecials = 16384;   // 32 R above this: host sort (all-pairs ranking is quadratic)
 
 }  // namespace debwt
 
@@ -145,38 +149,6 @@ void reset_input(debwt_ctx* c) {
     c->d_dollar = nullptr;
     c->built = false;
     c->stats = debwt_stats{};
-}
-
-// ---------------------------------------------------------------------------------------------
-// sentinel-window suffixes on the host (reference src/collect#$.c:131-157, 228-311, 348-602)
-// ---------------------------------------------------------------------------------------------
-struct HostText {
-    const u64* w;
-    const std::vector<u64>* seps;
-    u64 rec_of(u64 p) const { return (u64)(std::lower_bound(seps->begin(), seps->end(), p) - seps->begin()); }
-};
-
-// true suffix order under A<C<G<T<#<$; equal '#' are compared through, '$' is largest
-// (reference cmp, src/collect#$.c:253-311)
-bool special_less(const HostText& t, u64 pa, u64 pb) {
-    if (pa == pb) return false;
-    const u64 R = t.seps->size();
-    u64 ra = t.rec_of(pa), rb = t.rec_of(pb);
-    for (;;) {
-        const u64 da = (*t.seps)[ra] - pa, db = (*t.seps)[rb] - pb;
-        const u64 m = da < db ? da : db;
-        for (u64 off = 0; off < m; off += 32) {
-            u64 wa = text_window32(t.w, pa + off), wb = text_window32(t.w, pb + off);
-            const u64 len = m - off;
-            if (len < 32) { const u64 mask = ~(~0ull >> (2 * len)); wa &= mask; wb &= mask; }
-            if (wa != wb) return wa < wb;
-        }
-        if (da != db) return da > db;            // the side that reaches its separator first is larger
-        const bool a_end = (ra + 1 == R), b_end = (rb + 1 == R);
-        if (a_end || b_end) return !a_end && b_end;
-        pa = (*t.seps)[ra] + 1; pb = (*t.seps)[rb] + 1;
-        ++ra; ++rb;
-    }
 }
 
 }  // namespace
@@ -379,37 +351,64 @@ int debwt_build(debwt_ctx* c, int k) {
     pool.release(d_brws);
     mark();                                                                     // ev4
 
-    // ---- sentinel-window suffixes (host sort of 32 R suffixes over the packed text) ----
+    // ---- sentinel-window suffixes: ranked on the device (32 R suffixes, all pairs), tables built on the host ----
     const u64 nspec = 32 * R;
-    std::vector<u64> h_text(text_words(n));
-    CUDA_TRY(cudaMemcpyAsync(h_text.data(), d_text, h_text.size() * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    HostText ht{h_text.data(), &c->seps};
-    std::vector<Special> sp(nspec);
-    for (u64 r = 0, t = 0; r < R; ++r)
-        for (u32 j = 0; j < 32; ++j, ++t) {
-            sp[t].pos = c->seps[r] - j; sp[t].j = j; sp[t].rec = (u32)r; sp[t].emit = false;
+    std::vector<SpecialInfo> info(nspec);
+    std::vector<u64> h_ins(nspec);
+    u64* d_ins = nullptr;
+    if (dalloc(pool, &d_ins, nspec)) return -1;
+    if (nspec <= kMaxDeviceSpecials) {
+        SpecialInfo* d_info = nullptr;
+        if (dalloc(pool, &d_info, nspec)) return -1;
+        if (k_special_scan(d_text, d_seps, R, d_keys, nk, ki, d_info, st)) return -1;
+        CUDA_TRY(cudaMemcpyAsync(info.data(), d_info, nspec * sizeof(SpecialInfo), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        pool.release(d_info);
+    } else {
+        // many records: sort on the host over a copy of the packed text (reference: qsort, src/collect#$.c:157)
+        std::vector<u64> h_text(text_words(n));
+        CUDA_TRY(cudaMemcpyAsync(h_text.data(), d_text, h_text.size() * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<u32> order(nspec);
+        for (u64 t = 0; t < nspec; ++t) order[t] = (u32)t;
+        const u64* sp_seps = c->seps.data();
+        std::sort(order.begin(), order.end(), [&](u32 x, u32 y) {
+            return special_less(h_text.data(), sp_seps, R, sp_seps[x >> 5] - (x & 31), sp_seps[y >> 5] - (y & 31));
+        });
+        std::vector<u64> h_pads(nspec);
+        for (u64 i = 0; i < nspec; ++i) {
+            const u64 t = order[i], p = sp_seps[t >> 5] - (t & 31);
+            const u32 j = (u32)(t & 31);
+            SpecialInfo& o = info[t];
+            o.w0 = text_window32(h_text.data(), p);
+            o.w1 = text_window32(h_text.data(), p + j + 1);
+            o.rank = (u32)i;
+            o.prev = (u8)text_symbol(h_text.data(), p - 1);
+            o.next = (u8)text_symbol(h_text.data(), p + 31);
+            h_pads[t] = j ? ((o.w0 & ~(~0ull >> (2 * j))) | (~0ull >> (2 * j))) : ~0ull;
         }
-    std::sort(sp.begin(), sp.end(), [&](const Special& a, const Special& b) { return special_less(ht, a.pos, b.pos); });
-    std::vector<u64> h_pads(nspec), h_ins(nspec);
-    for (u64 t = 0; t < nspec; ++t) {
-        const u32 j = sp[t].j;
-        const u64 w = text_window32(h_text.data(), sp[t].pos);
-        h_pads[t] = j ? ((w & ~(~0ull >> (2 * j))) | (~0ull >> (2 * j))) : ~0ull;   // T padding (src/collect#$.c:428-455)
-        sp[t].chr = (u8)text_symbol(h_text.data(), sp[t].pos - 1);
+        u64* d_pads = nullptr;
+        if (dalloc(pool, &d_pads, nspec)) return -1;
+        CUDA_TRY(cudaMemcpyAsync(d_pads, h_pads.data(), nspec * 8, cudaMemcpyHostToDevice, st));
+        if (k_special_insertion(d_keys, nk, ki, d_pads, nspec, d_ins, st)) return -1;
+        CUDA_TRY(cudaMemcpyAsync(h_ins.data(), d_ins, nspec * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        pool.release(d_pads);
+        for (u64 t = 0; t < nspec; ++t) info[t].ins = (t & 31) ? h_ins[t] : nk;
     }
-    u64 *d_pads = nullptr, *d_ins = nullptr;
-    if (dalloc(pool, &d_pads, nspec) || dalloc(pool, &d_ins, nspec)) return -1;
-    CUDA_TRY(cudaMemcpyAsync(d_pads, h_pads.data(), nspec * 8, cudaMemcpyHostToDevice, st));
-    if (k_special_insertion(d_keys, nk, ki, d_pads, nspec, d_ins, st)) return -1;
-    CUDA_TRY(cudaMemcpyAsync(h_ins.data(), d_ins, nspec * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<Special> sp(nspec);
+    for (u64 t = 0; t < nspec; ++t) {
+        const SpecialInfo& o = info[t];
+        if (o.rank >= nspec) FAIL("internal: special suffix ranks are not a permutation");
+        Special& x = sp[o.rank];
+        x.pos = c->seps[t >> 5] - (t & 31); x.j = (u32)(t & 31); x.rec = (u32)(t >> 5); x.emit = false;
+        x.ins = o.ins; x.chr = o.prev; x.w0 = o.w0; x.w1 = o.w1; x.next = o.next;
+    }
     std::vector<u64> h_rows(nspec);
     std::vector<u8> h_chr(nspec);
     for (u64 t = 0; t < nspec; ++t) {
-        if (sp[t].j == 0) h_ins[t] = nk;                  // suffixes that start with a separator are the last R rows
+        h_ins[t] = sp[t].ins;
         if (t && h_ins[t] < h_ins[t - 1]) FAIL("internal: special insertion points are not monotone");
-        sp[t].ins = h_ins[t];
         sp[t].row = h_ins[t] + t;
         h_rows[t] = sp[t].row;
         h_chr[t] = sp[t].chr;
@@ -424,21 +423,20 @@ int debwt_build(debwt_ctx* c, int k) {
             const u32 j = sp[t].j;
             if (j == 31) { sp[t].emit = true; h_tail_pos[sp[t].rec] = sp[t].pos; continue; }
             if (sp[t].rec + 1 == R) continue;
-            const u64 p = sp[t].pos;
-            const u64 before = j ? (text_window32(h_text.data(), p) & ~(~0ull >> (2 * j))) : 0;
-            const u64 after = text_window32(h_text.data(), p + j + 1) & ~(~0ull >> (2 * (30 - j)));   // 30-j bases (>=0)
+            const u64 before = j ? (sp[t].w0 & ~(~0ull >> (2 * j))) : 0;
+            const u64 after = sp[t].w1 & ~(~0ull >> (2 * (30 - j)));                                  // 30-j bases (>=0)
             groups[std::make_tuple(j, before, j == 30 ? 0 : after)].push_back(t);
         }
         for (auto& g : groups) {
             if (g.second.size() < 2) continue;
             u32 seen = 0;
-            for (u64 t : g.second) seen |= 1u << text_symbol(h_text.data(), sp[t].pos + 31);
+            for (u64 t : g.second) seen |= 1u << sp[t].next;
             if (seen & (seen - 1))
                 for (u64 t : g.second) sp[t].emit = true;
         }
         for (u64 t = 0; t < nspec; ++t) if (sp[t].emit) h_emit_pos.push_back(sp[t].pos);
     }
-    u64 *d_rows = nullptr, *d_emit = nullptr, *d_tail = nullptr, *d_tail_idx = nullptr;
+    u64 *d_rows = nullptr, *d_emit = nullptr, *d_tail = nullptr, *d_tail_idx = nullptr, *d_pads = nullptr;
     u8* d_chr = nullptr;
     if (dalloc(pool, &d_rows, nspec) || dalloc(pool, &d_chr, nspec) || dalloc(pool, &d_emit, h_emit_pos.size() + 1) ||
         dalloc(pool, &d_tail, R) || dalloc(pool, &d_tail_idx, R))

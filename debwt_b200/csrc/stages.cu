@@ -1,6 +1,7 @@
 // Device stages around the radix sort: packing, extraction, count-by-sort, branch k-mer detection,
 // branch codes, emission.  Each kernel cites the reference loop it replaces.
 #include "stages.cuh"
+#include "special.cuh"
 
 namespace debwt {
 
@@ -468,6 +469,48 @@ int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, 
 
 int k_branch_index(BranchTable bt, cudaStream_t st) {
     branch_index_kernel<<<grid_for(bt.n_branch + 1, TPB), TPB, 0, st>>>(bt);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(128) special_scan_kernel(const u64* __restrict__ words, const u64* __restrict__ seps,
+                                                          u64 n_rec, const u64* __restrict__ k, u64 n_keys, KeyIndex ki,
+                                                          SpecialInfo* __restrict__ out) {
+    __shared__ u32 s_cnt;
+    const u64 m = n_rec * 32;
+    const u64 a = blockIdx.x;
+    const u64 pa = seps[a >> 5] - (a & 31);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    u32 cnt = 0;
+    for (u64 b = threadIdx.x; b < m; b += blockDim.x) {
+        if (b == a) continue;
+        const u64 pb = seps[b >> 5] - (b & 31);
+        cnt += special_less(words, seps, n_rec, pb, pa) ? 1u : 0u;
+    }
+    if (cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 j = (u32)(a & 31);
+        SpecialInfo o;
+        o.w0 = text_window32(words, pa);
+        o.w1 = text_window32(words, pa + j + 1);
+        o.rank = s_cnt;
+        o.prev = (u8)text_symbol(words, pa - 1);
+        o.next = (u8)text_symbol(words, pa + 31);
+        o.pad_[0] = o.pad_[1] = 0;
+        // T padding (src/collect#$.c:428-455): j bases then T's; suffixes that start with a separator sort last
+        o.ins = j ? indexed_upper_bound(k, ki, (o.w0 & ~(~0ull >> (2 * j))) | (~0ull >> (2 * j))) : n_keys;
+        out[a] = o;
+    }
+}
+}  // namespace
+
+int k_special_scan(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n_keys, KeyIndex ki,
+                   SpecialInfo* out, cudaStream_t st) {
+    special_scan_kernel<<<(unsigned)(n_rec * 32), 128, 0, st>>>(words, d_seps, n_rec, sorted, n_keys, ki, out);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -173,6 +173,25 @@ def test_bwt_large_segments_vs_oracle():
     assert all((a == b_).all() for a, b_ in zip(want, got))
 
 
+@pytest.mark.parametrize("n_rec", [40, 513, 700])
+def test_bwt_many_short_records(n_rec):
+    # 32 R sentinel-window suffixes: device all-pairs ranking up to 16384, host sort beyond
+    rng = random.Random(n_rec)
+    base = rnd(rng, 60)
+    recs = []
+    for i in range(n_rec):
+        if i % 3 == 0:
+            recs.append(rnd(rng, rng.randint(33, 70)))
+        else:
+            r = list(base[:rng.randint(33, 60)])
+            r[rng.randrange(len(r))] = rng.choice("ACGT")
+            recs.append("".join(r))
+    sym, _ = st.text_from_records(recs)
+    want = coracle.bwt(sym)
+    got = api.build_bwt(recs)
+    assert all((a == b).all() for a, b in zip(want, got))
+
+
 def test_bwt_errors():
     with pytest.raises(DebwtError):
         api.build_bwt(["ACGT" * 8])                 # 32 bp: "Length <= 32!" (src/collect#$.c:41-45)
