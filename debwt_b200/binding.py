@@ -56,9 +56,12 @@ _SIGS = {
 _lib = None
 
 
-def declared_symbols():
-    """Every function name include/debwt_b200.h declares."""
-    with open(HEADER) as f:
+DEV_HEADER = os.path.join(os.path.dirname(HERE), "include", "debwt_b200_dev.h")
+
+
+def declared_symbols(header: str = HEADER):
+    """Every function name the given header declares."""
+    with open(header) as f:
         src = f.read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(debwt_[a-z0-9_]+)\s*\(", src)))

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/debwt_b200.h"
+#include "../../include/debwt_b200_dev.h"
 #include "radix_sort.cuh"
 #include "stages.cuh"
 #include "special.cuh"
@@ -68,6 +69,56 @@ struct Special {
 };
 
 constexpr u64 kMaxDeviceSpecials = 16384;   // 32 R above this: host sort (all-pairs ranking is quadratic)
+
+
+// Host part of the sentinel-window handling: from the per-suffix scan results (rank, windows, insertion
+// point) to the tables the kernels consume.  `info[t]`, t = rec*32 + j.  Outputs are in suffix order.
+//   ins      : insertion points (ascending) -- overwritten with info[].ins in suffix order
+//   rows     : BWT row of each special suffix = ins + its rank
+//   chr      : its BWT symbol
+//   emit_pos : positions that emit a branch code (divideKmer, src/collect#$.c:537-598): tails always
+//              (src/INandOut.c:260-266); windows holding '#' when their 31-symbol prefix occurs with
+//              >= 2 different next symbols.  Windows holding '$' are unique.
+//   tail_pos : per record, the position of its tail k-mer
+int build_special_tables(const SpecialInfo* info, const u64* seps, u64 R, std::vector<u64>& ins, std::vector<u64>& rows,
+                         std::vector<u8>& chr, std::vector<u64>& emit_pos, std::vector<u64>& tail_pos) {
+    const u64 nspec = 32 * R;
+    std::vector<Special> sp(nspec);
+    std::vector<char> seen_rank(nspec, 0);
+    for (u64 t = 0; t < nspec; ++t) {
+        const SpecialInfo& o = info[t];
+        if (o.rank >= nspec || seen_rank[o.rank]) FAIL("internal: special suffix ranks are not a permutation");
+        seen_rank[o.rank] = 1;
+        Special& x = sp[o.rank];
+        x.pos = seps[t >> 5] - (t & 31); x.j = (u32)(t & 31); x.rec = (u32)(t >> 5); x.emit = false;
+        x.ins = o.ins; x.chr = o.prev; x.w0 = o.w0; x.w1 = o.w1; x.next = o.next;
+    }
+    ins.resize(nspec); rows.resize(nspec); chr.resize(nspec); tail_pos.assign(R, 0); emit_pos.clear();
+    for (u64 t = 0; t < nspec; ++t) {
+        ins[t] = sp[t].ins;
+        if (t && ins[t] < ins[t - 1]) FAIL("internal: special insertion points are not monotone");
+        rows[t] = ins[t] + t;
+        chr[t] = sp[t].chr;
+    }
+    std::map<std::tuple<u32, u64, u64>, std::vector<u64>> groups;
+    for (u64 t = 0; t < nspec; ++t) {
+        const u32 j = sp[t].j;
+        if (j == 31) { sp[t].emit = true; tail_pos[sp[t].rec] = sp[t].pos; continue; }
+        if (sp[t].rec + 1 == R) continue;
+        const u64 before = j ? (sp[t].w0 & ~(~0ull >> (2 * j))) : 0;
+        const u64 after = sp[t].w1 & ~(~0ull >> (2 * (30 - j)));                                  // 30-j bases (>=0)
+        groups[std::make_tuple(j, before, j == 30 ? 0 : after)].push_back(t);
+    }
+    for (auto& g : groups) {
+        if (g.second.size() < 2) continue;
+        u32 seen = 0;
+        for (u64 t : g.second) seen |= 1u << sp[t].next;
+        if (seen & (seen - 1))
+            for (u64 t : g.second) sp[t].emit = true;
+    }
+    for (u64 t = 0; t < nspec; ++t) if (sp[t].emit) emit_pos.push_back(sp[t].pos);
+    return 0;
+}
 
 }  // namespace debwt
 
@@ -396,46 +447,9 @@ int debwt_build(debwt_ctx* c, int k) {
         pool.release(d_pads);
         for (u64 t = 0; t < nspec; ++t) info[t].ins = (t & 31) ? h_ins[t] : nk;
     }
-    std::vector<Special> sp(nspec);
-    for (u64 t = 0; t < nspec; ++t) {
-        const SpecialInfo& o = info[t];
-        if (o.rank >= nspec) FAIL("internal: special suffix ranks are not a permutation");
-        Special& x = sp[o.rank];
-        x.pos = c->seps[t >> 5] - (t & 31); x.j = (u32)(t & 31); x.rec = (u32)(t >> 5); x.emit = false;
-        x.ins = o.ins; x.chr = o.prev; x.w0 = o.w0; x.w1 = o.w1; x.next = o.next;
-    }
-    std::vector<u64> h_rows(nspec);
-    std::vector<u8> h_chr(nspec);
-    for (u64 t = 0; t < nspec; ++t) {
-        h_ins[t] = sp[t].ins;
-        if (t && h_ins[t] < h_ins[t - 1]) FAIL("internal: special insertion points are not monotone");
-        sp[t].row = h_ins[t] + t;
-        h_rows[t] = sp[t].row;
-        h_chr[t] = sp[t].chr;
-    }
-    // which sentinel-window positions emit a branch code (divideKmer, src/collect#$.c:537-598):
-    // tails always (src/INandOut.c:260-266); windows holding '#' when their 31-symbol prefix occurs with
-    // >= 2 different next symbols.  Windows holding '$' are unique.
-    std::vector<u64> h_emit_pos, h_tail_pos(R);
-    {
-        std::map<std::tuple<u32, u64, u64>, std::vector<u64>> groups;
-        for (u64 t = 0; t < nspec; ++t) {
-            const u32 j = sp[t].j;
-            if (j == 31) { sp[t].emit = true; h_tail_pos[sp[t].rec] = sp[t].pos; continue; }
-            if (sp[t].rec + 1 == R) continue;
-            const u64 before = j ? (sp[t].w0 & ~(~0ull >> (2 * j))) : 0;
-            const u64 after = sp[t].w1 & ~(~0ull >> (2 * (30 - j)));                                  // 30-j bases (>=0)
-            groups[std::make_tuple(j, before, j == 30 ? 0 : after)].push_back(t);
-        }
-        for (auto& g : groups) {
-            if (g.second.size() < 2) continue;
-            u32 seen = 0;
-            for (u64 t : g.second) seen |= 1u << sp[t].next;
-            if (seen & (seen - 1))
-                for (u64 t : g.second) sp[t].emit = true;
-        }
-        for (u64 t = 0; t < nspec; ++t) if (sp[t].emit) h_emit_pos.push_back(sp[t].pos);
-    }
+    std::vector<u64> h_rows, h_emit_pos, h_tail_pos;
+    std::vector<u8> h_chr;
+    if (build_special_tables(info.data(), c->seps.data(), R, h_ins, h_rows, h_chr, h_emit_pos, h_tail_pos)) return -1;
     u64 *d_rows = nullptr, *d_emit = nullptr, *d_tail = nullptr, *d_tail_idx = nullptr, *d_pads = nullptr;
     u8* d_chr = nullptr;
     if (dalloc(pool, &d_rows, nspec) || dalloc(pool, &d_chr, nspec) || dalloc(pool, &d_emit, h_emit_pos.size() + 1) ||
@@ -684,6 +698,25 @@ int debwt_k_group_masks(int device, const char* text, uint64_t n, const uint64_t
         return -1;
     CUDA_TRY(cudaMemcpyAsync(masks_out, d_g, nk * 2, cudaMemcpyDeviceToHost, s.st));
     CUDA_TRY(cudaStreamSynchronize(s.st));
+    return 0;
+}
+
+int debwt_special_tables(const void* info_host, const uint64_t* ins_by_t, const uint64_t* seps, uint64_t n_rec,
+                         uint64_t* ins_out, uint64_t* rows_out, uint8_t* chr_out, uint64_t* emit_pos_out,
+                         uint64_t* n_emit_out, uint64_t* tail_pos_out) {
+    const u64 nspec = 32 * n_rec;
+    std::vector<SpecialInfo> info(reinterpret_cast<const SpecialInfo*>(info_host),
+                                  reinterpret_cast<const SpecialInfo*>(info_host) + nspec);
+    for (u64 t = 0; t < nspec; ++t) info[t].ins = ins_by_t[t];
+    std::vector<u64> seps64(seps, seps + n_rec), ins, rows, emit, tail;
+    std::vector<u8> chr;
+    if (build_special_tables(info.data(), seps64.data(), n_rec, ins, rows, chr, emit, tail)) return -1;
+    std::copy(ins.begin(), ins.end(), ins_out);
+    std::copy(rows.begin(), rows.end(), rows_out);
+    std::copy(chr.begin(), chr.end(), chr_out);
+    std::copy(emit.begin(), emit.end(), emit_pos_out);
+    std::copy(tail.begin(), tail.end(), tail_pos_out);
+    *n_emit_out = emit.size();
     return 0;
 }
 

@@ -2,6 +2,8 @@
 // branch codes, emission.  Each kernel cites the reference loop it replaces.
 #include "stages.cuh"
 #include "special.cuh"
+#include "stages_dev.cuh"
+#include "dist_kernels.cuh"
 
 namespace debwt {
 
@@ -146,10 +148,6 @@ __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii,
 // =============================================================================================
 // K2: (k+1)-mer extraction                   (Jellyfish count, src/kmercounting.sh:8; src/mySort.c:54-83)
 // =============================================================================================
-__device__ __forceinline__ u64 record_of(const u64* __restrict__ seps, u64 n_rec, u64 p) {
-    return lower_bound_u64(seps, 0, n_rec, p);     // number of separators strictly before p
-}
-
 __global__ void __launch_bounds__(TPB) extract_kernel(const u64* __restrict__ words, u64 n,
                                                      const u64* __restrict__ seps, u64 n_rec,
                                                      u64* __restrict__ keys) {
@@ -209,6 +207,14 @@ int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st) {
     return 0;
 }
 
+int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cudaStream_t st) {
+    if (nwords == 0) return 0;
+    pack_kernel<<<grid_for(nwords, TPB), TPB, 0, st>>>(ascii, n, words, nwords, d_err);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st) {
     extract_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(words, n, d_seps, n_rec, keys);
     DEBWT_COUNT(1);
@@ -254,32 +260,6 @@ int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u6
 // K5/K6: in/out edges per k-mer group         (src/getKmer.c:62-120, src/INandOut.c:260-343)
 // =============================================================================================
 namespace {
-
-// first index of the group (k-mer = key >> 2) that sorted[i] belongs to
-__device__ __forceinline__ u64 group_head(const u64* __restrict__ k, u64 i) {
-    const u64 x = k[i] >> 2;
-    u64 hi = i, step = 1, lo;
-    for (;;) {
-        if (step > hi) { lo = 0; break; }
-        u64 j = hi - step;
-        if ((k[j] >> 2) == x) { hi = j; step <<= 1; }
-        else { lo = j + 1; break; }
-    }
-    return lower_bound_u64(k, lo, hi, x << 2);
-}
-
-// one past the last index of the group that sorted[i] belongs to
-__device__ __forceinline__ u64 group_end(const u64* __restrict__ k, u64 n, u64 i) {
-    const u64 x = k[i] >> 2;
-    u64 lo = i, step = 1, hi;
-    for (;;) {
-        u64 j = lo + step;
-        if (j >= n) { hi = n; break; }
-        if ((k[j] >> 2) == x) { lo = j; step <<= 1; }
-        else { hi = j; break; }
-    }
-    return upper_bound_u64(k, lo, hi, (x << 2) | 3ull);
-}
 
 __global__ void __launch_bounds__(TPB) key_index_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki) {
     const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
@@ -529,18 +509,6 @@ int k_special_insertion(const u64* sorted, u64 n, KeyIndex ki, const u64* pads, 
 // =============================================================================================
 namespace {
 
-__device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-mer << 2, low bits 0 */, u64& b) {
-    const u64 t = x >> (64 - bt.bits);
-    u64 lo = bt.bidx[t], hi = bt.bidx[t + 1];
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        u64 v = bt.kmer[mid] & ~3ull;
-        if (v < x) lo = mid + 1; else hi = mid;
-    }
-    if (lo < bt.n_branch && (bt.kmer[lo] & ~3ull) == x) { b = lo; return true; }
-    return false;
-}
-
 __global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restrict__ words, u64 n,
                                                             const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
                                                             u32* __restrict__ mo_bits, u64* __restrict__ blue) {
@@ -598,11 +566,6 @@ __global__ void __launch_bounds__(TPB) emit_codes_kernel(const u64* __restrict__
         ++c;
     }
     if (acc) atomicOr(sp_codes + acc_word, acc);
-}
-
-__device__ __forceinline__ u64 sp_index_of(const u32* __restrict__ mo_bits, const u32* __restrict__ word_prefix, u64 p) {
-    const u32 bits = mo_bits[p >> 5];
-    return (u64)word_prefix[p >> 5] + __popc(bits & ((1u << (p & 31)) - 1u));
 }
 
 __global__ void __launch_bounds__(TPB) mark_sep_codes_kernel(const u32* __restrict__ mo_bits, const u32* __restrict__ word_prefix,
@@ -706,10 +669,6 @@ __global__ void __launch_bounds__(TPB) fill_case2_kernel(const u16* __restrict__
         const u32 lo32 = __reduce_or_sync(0xffffffffu, lane >= 16 ? code << (2 * (31 - lane)) : 0u);
         if (lane == 0) bwt[w] = ((u64)hi32 << 32) | lo32;
     }
-}
-
-__device__ __forceinline__ void bwt_or(u64* __restrict__ bwt, u64 row, u32 code) {
-    atomicOr(bwt + (row >> 5), (u64)code << (2 * (31 - (row & 31))));
 }
 
 __global__ void __launch_bounds__(TPB) emit_blue_kernel(const u64* __restrict__ blue, BranchTable bt,

@@ -1,0 +1,63 @@
+// Small device helpers shared by the single-GPU stages (stages.cu) and the sharded stages (dist_kernels.cu).
+#pragma once
+#include "stages.cuh"
+
+namespace debwt {
+
+__device__ __forceinline__ u64 record_of(const u64* __restrict__ seps, u64 n_rec, u64 p) {
+    return lower_bound_u64(seps, 0, n_rec, p);     // number of separators strictly before p
+}
+
+
+// first index of the group (k-mer = key >> 2) that sorted[i] belongs to
+__device__ __forceinline__ u64 group_head(const u64* __restrict__ k, u64 i) {
+    const u64 x = k[i] >> 2;
+    u64 hi = i, step = 1, lo;
+    for (;;) {
+        if (step > hi) { lo = 0; break; }
+        u64 j = hi - step;
+        if ((k[j] >> 2) == x) { hi = j; step <<= 1; }
+        else { lo = j + 1; break; }
+    }
+    return lower_bound_u64(k, lo, hi, x << 2);
+}
+
+// one past the last index of the group that sorted[i] belongs to
+__device__ __forceinline__ u64 group_end(const u64* __restrict__ k, u64 n, u64 i) {
+    const u64 x = k[i] >> 2;
+    u64 lo = i, step = 1, hi;
+    for (;;) {
+        u64 j = lo + step;
+        if (j >= n) { hi = n; break; }
+        if ((k[j] >> 2) == x) { lo = j; step <<= 1; }
+        else { hi = j; break; }
+    }
+    return upper_bound_u64(k, lo, hi, (x << 2) | 3ull);
+}
+
+
+__device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-mer << 2, low bits 0 */, u64& b) {
+    const u64 t = x >> (64 - bt.bits);
+    u64 lo = bt.bidx[t], hi = bt.bidx[t + 1];
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        u64 v = bt.kmer[mid] & ~3ull;
+        if (v < x) lo = mid + 1; else hi = mid;
+    }
+    if (lo < bt.n_branch && (bt.kmer[lo] & ~3ull) == x) { b = lo; return true; }
+    return false;
+}
+
+
+__device__ __forceinline__ u64 sp_index_of(const u32* __restrict__ mo_bits, const u32* __restrict__ word_prefix, u64 p) {
+    const u32 bits = mo_bits[p >> 5];
+    return (u64)word_prefix[p >> 5] + __popc(bits & ((1u << (p & 31)) - 1u));
+}
+
+
+__device__ __forceinline__ void bwt_or(u64* __restrict__ bwt, u64 row, u32 code) {
+    atomicOr(bwt + (row >> 5), (u64)code << (2 * (31 - (row & 31))));
+}
+
+
+}  // namespace debwt

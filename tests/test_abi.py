@@ -17,6 +17,14 @@ def test_library_exports_every_declared_symbol():
     assert set(binding._SIGS) == set(names)
 
 
+def test_library_exports_every_device_stage_symbol():
+    L = binding.lib()
+    names = binding.declared_symbols(binding.DEV_HEADER)
+    assert len(names) >= 26
+    for n in names:
+        assert hasattr(L, n), n
+
+
 def test_stats_struct_matches_header_layout():
     # 7 u64 + 12 float + 3 u32 = 56 + 48 + 12 = 116 -> padded to 120
     assert ctypes.sizeof(binding.Stats) == 120
