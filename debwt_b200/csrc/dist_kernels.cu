@@ -347,8 +347,8 @@ int k_apply_in_queries(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, const 
 
 int k_flag_slice(const u64* words, u64 pos_lo, u64 pos_hi, const u64* d_seps, u64 n_rec, BranchTable bt, u32* mo_bits,
                  u64* rec_entry, u64* rec_index, u64* d_rec_count, cudaStream_t st) {
+    if (pos_hi <= pos_lo) return 0;                  // mo_bits stays as the caller zeroed it
     const u64 npos = (pos_hi - pos_lo + 31) & ~31ull;
-    if (npos == 0) return 0;
     flag_slice_kernel<<<grid_for(npos, TPB), TPB, 0, st>>>(words, pos_lo, pos_hi, d_seps, n_rec, bt, mo_bits, rec_entry,
                                                            rec_index, d_rec_count);
     LAUNCHED(1);

@@ -414,7 +414,7 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
     NK = N - 32 * R
     wp, wtot = slice_geometry(N, G)
     pos_lo, pos_hi_al = 32 * r * wp, 32 * (r + 1) * wp
-    pos_hi = min(pos_hi_al, N)
+    pos_hi = max(min(pos_hi_al, N), pos_lo)                 # a slice may lie entirely in the padding
     d_seps = ops.from_numpy(seps)
 
     # 1. pack own slice, all-gather the packed text
