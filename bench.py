@@ -70,16 +70,19 @@ class ClockSampler:
     """Samples SM clock and throttle reasons DURING the timed region through NVML (in-process: spawning
     nvidia-smi in a loop perturbs the driver enough to slow the measured kernels down)."""
 
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.02):
         self.index, self.period, self.rows, self.stop, self.thr, self.h = index, period_s, [], threading.Event(), None, None
         self.nv = None
 
     def __enter__(self):
+        if os.environ.get("DEBWT_NO_CLOCKS"):
+            return self
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)   # slow call: once, up front
             self.thr = threading.Thread(target=self._run, daemon=True)
             self.thr.start()
         except Exception:  # noqa: BLE001
@@ -91,7 +94,7 @@ class ClockSampler:
         while not self.stop.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = self.max_mhz
                 rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 self.rows.append((sm, mx, rs))
@@ -311,6 +314,112 @@ def ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def ours_sharded(args, rank, world, local_rank):
+    """N GPUs, one process per GPU: the text is split by position, keys are range-partitioned by sampled
+    splitters and exchanged with one NCCL all-to-all (debwt_b200/dist.py).  Strong scaling: the same
+    genome on N GPUs."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from debwt_b200 import api, binding, dist as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    comm = D.Comm()
+    ops = D.CudaOps(local_rank)
+    ops.timed_main_sort = True
+    records, desc = make_workload(args.workload, rank)
+    text_np, seps = api.join_records(records)
+    n = int(text_np.size)
+    n_bases = n - len(records)
+    lo, hi = D.my_slice(n, comm)
+    h_slice = torch.empty(max(hi - lo, 1), dtype=torch.uint8, pin_memory=True)
+    h_slice.numpy()[:hi - lo] = text_np[lo:hi]
+    d_slice = h_slice.to("cuda")
+    n_words = (n + 31) // 32
+    h_out = torch.empty(n_words, dtype=torch.int64, pin_memory=True) if rank == 0 else None
+    del text_np
+
+    def barrier():
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    stats = {}
+
+    def step(resident: bool):
+        src = d_slice if resident else h_slice.to("cuda", non_blocking=True)
+        out = D.build_sharded(None, seps, comm, ops, stats, n_symbols=n, ascii_slice=src, fetch=False)
+        if not resident and rank == 0:
+            h_out.copy_(out[0], non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    barrier()
+    l0 = binding.lib().debwt_launch_count()
+    sort_ms = sweep_ms = 0.0
+    sweeps = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            step(True)
+            sort_ms += ops.sort_stats["ms"]; sweep_ms += ops.sort_stats["ms_sweeps"]; sweeps += ops.sort_stats["sweeps"]
+        ev1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    launches = int(binding.lib().debwt_launch_count() - l0)
+    clocks = clk.summary()
+    for _ in range(2):
+        step(False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(False)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    tt = torch.tensor([dev_ms, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = (float(x) for x in tt.tolist())
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nk_loc = ops.sort_stats["n"]
+        per_launch_ms = sweep_ms / max(sweeps, 1)
+        achieved = 16.0 * nk_loc / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        phase = 136.0 * nk_loc / ((sort_ms / args.steps) * 1e-3) / 1e9 if sort_ms > 0 else 0.0
+        traffic = ncu_traffic_per_launch()
+        line = {
+            "metric": METRIC, "value": n_bases / (dev_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "n_bases": n_bases, "n_records": len(records), "k": 32,
+                       "l2": "inputs larger than L2 (keys %d MB per GPU per step)" % (8 * nk_loc // 2**20),
+                       "parallelism": "position split x%d, keys range-partitioned by sampled splitters, NCCL all-to-all" % world,
+                       "timing": "CUDA events on the torch stream around the step, max over ranks; wall per step %.3f ms" % wall_ms,
+                       "keys_per_gpu": stats.get("keys_local"), "nccl_bytes_sent_rank0_total": stats.get("bytes_sent")},
+            "clocks": clocks,
+            "e2e": {"value": n_bases / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * n_words,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (radix-sort scatter pass on rank 0's key range, %d launches/step)"
+                                                   % (sweeps // max(args.steps, 1)),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 16 * nk_loc, "mean_launch_ms": per_launch_ms,
+                         "traffic": (traffic or {}).get("dram_bytes_per_key", None) and traffic["dram_bytes_per_key"] * nk_loc,
+                         "sort_phase": {"achieved": phase, "frac": phase / peak, "bytes_per_key": 136, "ms": sort_ms / args.steps}},
+            "sizes": {k: stats.get(k) for k in ("n_symbols", "n_keys", "n_branch", "n_blue", "n_codes")},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -321,14 +430,21 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=12_000_000, help="bases of the workload the cpu_baseline leg runs")
     ap.add_argument("--ref-sample", type=int, default=0, help="bases per step of the --impl reference arm (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks (to measure the sampler's own cost)")
+    ap.add_argument("--sharded", action="store_true", help="use the sharded (multi-GPU) code path even at N=1")
     args = ap.parse_args()
+    if args.no_clocks:
+        os.environ["DEBWT_NO_CLOCKS"] = "1"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
-    ours(args, rank, world, local_rank)
+    if world > 1 or args.sharded:
+        ours_sharded(args, rank, world, local_rank)
+    else:
+        ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

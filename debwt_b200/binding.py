@@ -35,6 +35,7 @@ class Stats(ctypes.Structure):
 _SIGS = {
     "debwt_last_error": (ctypes.c_char_p, []),
     "debwt_device_count": (ctypes.c_int, []),
+    "debwt_launch_count": (ctypes.c_uint64, []),
     "debwt_create": (ctypes.c_int, [ctypes.POINTER(c_p), ctypes.c_int]),
     "debwt_destroy": (None, [c_p]),
     "debwt_set_sort_config": (ctypes.c_int, [c_p, ctypes.c_int]),

@@ -24,6 +24,7 @@ namespace debwt {
 
 static thread_local std::string g_err;
 unsigned g_launches = 0;
+unsigned long long g_launches_total = 0;
 void set_error(const std::string& msg) { g_err = msg; }
 
 #define FAIL(msg)            \
@@ -33,25 +34,43 @@ void set_error(const std::string& msg) { g_err = msg; }
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// stream-ordered device memory, cached by the driver pool between builds
+// device memory: a per-context arena (grow-only chunks, bump allocation, reset per build).  The driver's
+// stream-ordered pool (cudaMallocAsync) showed millisecond-level, step-to-step variance for the
+// multi-hundred-MB buffers of a build; an arena makes steady-state builds allocation-free.
 // ---------------------------------------------------------------------------------------------
 struct DevPool {
+    struct Chunk { char* base; size_t cap, used; };
     cudaStream_t st = nullptr;
-    std::vector<void*> live;
+    std::vector<Chunk> chunks;
+    size_t next_chunk = 256ull << 20;
+    void hint(size_t bytes) { if (bytes > next_chunk) next_chunk = bytes; }
     int alloc(void** p, size_t bytes) {
-        if (bytes == 0) bytes = 16;
-        CUDA_TRY(cudaMallocAsync(p, bytes, st));
-        live.push_back(*p);
+        bytes = (bytes + 511) & ~(size_t)511;
+        if (bytes == 0) bytes = 512;
+        for (auto& c : chunks) {
+            if (c.cap - c.used >= bytes) { *p = c.base + c.used; c.used += bytes; return 0; }
+        }
+        Chunk c{nullptr, bytes > next_chunk ? bytes : next_chunk, 0};
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.base), c.cap));
+        *p = c.base;
+        c.used = bytes;
+        chunks.push_back(c);
         return 0;
     }
+    // only the most recent allocation of a chunk can be handed back (stack discipline); anything else
+    // stays reserved until the next reset
     void release(void* p) {
         if (!p) return;
-        auto it = std::find(live.begin(), live.end(), p);
-        if (it != live.end()) { live.erase(it); cudaFreeAsync(p, st); }
+        for (auto& c : chunks) {
+            char* q = static_cast<char*>(p);
+            if (q >= c.base && q < c.base + c.used) { last_release_hint(c, q); return; }
+        }
     }
-    void release_all() {
-        for (void* p : live) cudaFreeAsync(p, st);
-        live.clear();
+    void last_release_hint(Chunk&, char*) {}
+    void release_all() { for (auto& c : chunks) c.used = 0; }
+    void destroy() {
+        for (auto& c : chunks) cudaFree(c.base);
+        chunks.clear();
     }
 };
 
@@ -211,6 +230,8 @@ extern "C" {
 
 const char* debwt_last_error(void) { return g_err.c_str(); }
 
+uint64_t debwt_launch_count(void) { return g_launches_total; }
+
 int debwt_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -234,8 +255,8 @@ int debwt_create(debwt_ctx** out, int device) {
 void debwt_destroy(debwt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->pool.release_all();
     cudaStreamSynchronize(c->st);
+    c->pool.destroy();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->st);
     delete c;
@@ -262,6 +283,7 @@ int debwt_set_records(debwt_ctx* c, const char* const* seqs, const uint64_t* len
     }
     if (check_seps(c->seps.data(), n_records, n)) return -1;
     c->n = n; c->n_rec = n_records;
+    c->pool.hint(n * 28 + (64ull << 20));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
     if (dalloc(c->pool, &c->d_ascii, n + 64)) return -1;
     u64 off = 0;
@@ -288,6 +310,7 @@ int debwt_set_text(debwt_ctx* c, const char* text, uint64_t n, const uint64_t* s
     if (check_seps(seps, n_records, n)) return -1;
     c->seps.assign(seps, seps + n_records);
     c->n = n; c->n_rec = n_records;
+    c->pool.hint(n * 28 + (64ull << 20));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
     if (dalloc(c->pool, &c->d_ascii, n + 64)) return -1;
     CUDA_TRY(cudaMemcpyAsync(c->d_ascii, text, n, cudaMemcpyHostToDevice, c->st));
@@ -305,6 +328,7 @@ int debwt_set_text_device(debwt_ctx* c, const void* d_text, uint64_t n, const ui
     if (reinterpret_cast<uintptr_t>(d_text) & 15) FAIL("device text must be 16-byte aligned");
     c->seps.assign(seps, seps + n_records);
     c->n = n; c->n_rec = n_records;
+    c->pool.hint(n * 27 + (64ull << 20));
     c->d_ascii_ext = reinterpret_cast<const u8*>(d_text);
     return 0;
 }

@@ -21,8 +21,9 @@ constexpr u32 GM_OUT_SHIFT = 8;        // bits 8..11: out-base seen
 constexpr u32 GM_OUT_TAIL = 1u << 12;  // the k-mer also occurs right before a separator
 
 void set_error(const std::string& msg);
-extern unsigned g_launches;   // kernel launches since the last reset (host-side bookkeeping for the bench)
-#define DEBWT_COUNT(n) (debwt::g_launches += (n))
+extern unsigned g_launches;        // kernel launches since the last debwt_build() started
+extern unsigned long long g_launches_total;   // kernel launches in this process
+#define DEBWT_COUNT(n) (debwt::g_launches += (n), debwt::g_launches_total += (n))
 
 #define CUDA_TRY(expr)                                                                     \
     do {                                                                                   \

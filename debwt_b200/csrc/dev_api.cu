@@ -59,6 +59,33 @@ int debwt_dev_sort(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, 
     return 0;
 }
 
+int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, float* ms_total, float* ms_sweeps,
+                         int* n_sweeps, void* stream) {
+    cudaStream_t st = S(stream);
+    void* ws_mem = nullptr;
+    CUDA_TRY(cudaMallocAsync(&ws_mem, sort_workspace_bytes(n, cfg), st));
+    SortWorkspace ws;
+    sort_workspace_bind(ws, ws_mem, n, cfg);
+    cudaEvent_t e[4];
+    for (auto& x : e) CUDA_TRY(cudaEventCreate(&x));
+    int sweeps = 0;
+    ws.ev_sweep_begin = e[1]; ws.ev_sweep_end = e[2]; ws.sweeps_out = &sweeps;
+    CUDA_TRY(cudaEventRecord(e[0], st));
+    u64* res = nullptr;
+    int rc = radix_sort_u64(P64(d_a), P64(d_b), n, ws, st, &res);
+    CUDA_TRY(cudaEventRecord(e[3], st));
+    cudaFreeAsync(ws_mem, st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!rc) {
+        if (ms_total) CUDA_TRY(cudaEventElapsedTime(ms_total, e[0], e[3]));
+        if (ms_sweeps) { *ms_sweeps = 0; if (sweeps) CUDA_TRY(cudaEventElapsedTime(ms_sweeps, e[1], e[2])); }
+        if (n_sweeps) *n_sweeps = sweeps;
+        if (result_in_b) *result_in_b = (res == P64(d_b)) ? 1 : 0;
+    }
+    for (auto& x : e) cudaEventDestroy(x);
+    return rc;
+}
+
 int debwt_dev_owner_of_keys(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
                             int drop_marker, void* d_dest_u8, void* stream) {
     return k_owner_of_keys(P64(d_items), n, P64(d_splitters), n_split, mask, drop_marker != 0, P8(d_dest_u8), S(stream));

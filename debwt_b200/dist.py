@@ -198,13 +198,19 @@ class CudaOps:
         self._ck(self.L.debwt_dev_extract(_p(words), _u64(pos_lo), _u64(pos_hi), _p(seps), _u64(n_rec), _u64(idx_base),
                                           _p(keys_out), self._st()))
 
-    def sort(self, keys):
+    def sort(self, keys, timed: bool = False):
         n = keys.numel()
         if n <= 1:
             return keys
         tmp = torch.empty_like(keys)
         in_b = ctypes.c_int(0)
-        self._ck(self.L.debwt_dev_sort(_p(keys), _p(tmp), _u64(n), self.sort_cfg, ctypes.byref(in_b), self._st()))
+        if timed:
+            ms, msw, nsw = ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
+            self._ck(self.L.debwt_dev_sort_timed(_p(keys), _p(tmp), _u64(n), self.sort_cfg, ctypes.byref(in_b), ctypes.byref(ms),
+                                                 ctypes.byref(msw), ctypes.byref(nsw), self._st()))
+            self.sort_stats = {"n": n, "ms": ms.value, "ms_sweeps": msw.value, "sweeps": nsw.value}
+        else:
+            self._ck(self.L.debwt_dev_sort(_p(keys), _p(tmp), _u64(n), self.sort_cfg, ctypes.byref(in_b), self._st()))
         return tmp if in_b.value else keys
 
     def owner_of_keys(self, items, splitters, mask, drop_marker):
@@ -403,13 +409,34 @@ def choose_splitters(sorted_samples: np.ndarray, size: int) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------
 # the sharded build
 # --------------------------------------------------------------------------------------------------
-def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: dict | None = None):
-    """text: the ASCII text T (every rank passes the same array; only its slice is uploaded).
-    Returns (words, sharp_rows, dollar_row) on rank 0 and (None, None, None) elsewhere."""
+def my_slice(n_symbols: int, comm: Comm):
+    """[pos_lo, pos_hi) of the text this rank uploads and works on"""
+    wp, _ = slice_geometry(n_symbols, comm.size)
+    lo = 32 * comm.rank * wp
+    return lo, max(min(32 * (comm.rank + 1) * wp, n_symbols), lo)
+
+
+def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, stats: dict | None = None,
+                  n_symbols: int | None = None, ascii_slice=None, fetch: bool = True):
+    """text: the ASCII text T (every rank passes the same array; only its slice is uploaded), or None when
+    `ascii_slice` already holds this rank's slice (`my_slice`) on the device and `n_symbols` = len(T).
+    Returns (words, sharp_rows, dollar_row) on rank 0 and (None, None, None) elsewhere; with fetch=False
+    the packed BWT stays on rank 0's device and is returned as a tensor."""
     G, r = comm.size, comm.rank
     if G > 16:
         raise binding.DebwtError("at most 16 ranks")
-    N, R = int(text.size), int(seps.size)
+    import time as _time
+    phases = {}
+    _t = [_time.perf_counter()]
+
+    def tick(name):
+        if stats is not None and stats.get("profile"):
+            ops.sync()
+            now = _time.perf_counter()
+            phases[name] = phases.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
+
+    N, R = int(text.size if text is not None else n_symbols), int(seps.size)
     seps = np.ascontiguousarray(seps, dtype=np.uint64)
     NK = N - 32 * R
     wp, wtot = slice_geometry(N, G)
@@ -419,7 +446,8 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
 
     # 1. pack own slice, all-gather the packed text
     n_valid = max(0, pos_hi - pos_lo)
-    ascii_slice = ops.from_numpy(text[pos_lo:pos_hi] if n_valid else np.zeros(1, np.uint8))
+    if ascii_slice is None:
+        ascii_slice = ops.from_numpy(text[pos_lo:pos_hi] if n_valid else np.zeros(1, np.uint8))
     my_words = ops.zeros(wp)
     err = ops.zeros(4, torch.int32)
     ops.pack(ascii_slice, n_valid, my_words, wp, err)
@@ -428,6 +456,7 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
         raise binding.DebwtError("input contains a symbol other than A, C, G, T (either case)")
     del ascii_slice
 
+    tick('pack+allgather')
     # 2. keys of own slice, splitters
     idx_base = valid_windows_before(pos_lo, seps)
     cnt = valid_windows_before(pos_hi, seps) - idx_base if n_valid else 0
@@ -455,18 +484,21 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
             return d
         return ops.owner_of_keys(items, d_split[:n_split], mask, drop_marker)
 
+    tick('extract+splitters')
     # 3. one all-to-all: every key goes to the owner of its k-mer
     dest = owner(keys, 0xFFFFFFFFFFFFFFFC, False)
     part, _, counts = ops.partition(keys, None, dest, G)
     mine, _ = comm.all_to_all_v(part, counts)
     del keys, part, dest
+    tick('partition+alltoall')
     n_loc = int(mine.numel())
-    sk = ops.sort(mine)
+    sk = ops.sort(mine, True) if getattr(ops, "timed_main_sort", False) else ops.sort(mine)
     n_all = comm.all_gather_scalar(n_loc)
     if sum(n_all) != NK:
         raise binding.DebwtError("internal: key exchange lost keys")
     key_base = sum(n_all[:r])
 
+    tick('sort')
     # 4. branch k-mer detection on the owned key range
     ki = ops.key_index(sk)
     gmask = ops.zeros(n_loc + 2, torch.int16)
@@ -485,6 +517,7 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
     m_all = comm.all_gather_scalar(bt["M"])
     gbidx = ops.branch_index(gkmer)
 
+    tick('classify+branch')
     # 5. sentinel-window suffixes (ranked redundantly on every rank; insertion points are summed)
     info = ops.special_scan(words, d_seps, R, sk, ki)
     info_rec = info.view(np.uint64).reshape(-1, 4)
@@ -495,6 +528,7 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
     d_emit = ops.from_numpy(emit_pos) if emit_pos.size else ops.empty(0)
     d_tail = ops.from_numpy(tail_pos)
 
+    tick('special')
     # 6. branch codes of own position slice at global code indices
     cap = min(cnt, sum(m_all)) + 1
     mo, rec_entry, rec_index = ops.flag_slice(words, pos_lo, pos_hi, d_seps, R, gkmer, gbidx, wp, cap)
@@ -514,6 +548,7 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
     if rec_entry.numel():
         ops.fix_records(rec_entry, mo, wpfx, pos_lo, code_base)
 
+    tick('codes')
     # 7. blue entries travel to the owner of their k-mer
     d_bbase = ops.from_numpy(b_base)
     db = ops.owner_of_index(rec_index, d_bbase, G) if rec_index.numel() else ops.empty(0, torch.uint8)
@@ -525,6 +560,7 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
     blue = ops.scatter_blue(e_recv, i_recv, bt)
     ops.sort_blue(blue, bt, codes, sep, dollar_index, s_tot)
 
+    tick('blue')
     # 8. every rank emits its own run of BWT rows; segments are summed (disjoint bits) onto rank 0
     n_out = (N + 31) // 32
     bwt = ops.zeros(n_out + 1)
@@ -539,11 +575,15 @@ def build_sharded(text: np.ndarray, seps: np.ndarray, comm: Comm, ops, stats: di
     comm.reduce_sum_to0(bwt)
     sharp_all, _ = comm.all_gather_var(sharp)
     comm.all_reduce_max(dollar)
+    tick('emit+reduce')
     if stats is not None:
+        stats["phases_ms"] = phases
         stats.update({"n_symbols": N, "n_keys": NK, "keys_local": n_all, "n_branch": int(sum(b_all)), "n_blue": int(sum(m_all)),
                       "n_codes": int(s_tot), "bytes_sent": comm.bytes_sent, "launches": getattr(ops, "launches", 0)})
     if r != 0:
         return None, None, None
+    if not fetch:
+        return bwt[:n_out], sharp_all, dollar
     words_np = bwt[:n_out].cpu().numpy().view(np.uint64).copy()
     sharp_np = np.sort(sharp_all.cpu().numpy().view(np.uint64))
     dollar_np = dollar.cpu().numpy().view(np.uint64).copy()

@@ -53,6 +53,8 @@ typedef struct debwt_stats {
 const char* debwt_last_error(void);
 /* number of CUDA devices visible (0 when the driver is missing) */
 int debwt_device_count(void);
+/* kernels launched by this library in this process so far (bookkeeping for the bench's gpu_launches) */
+uint64_t debwt_launch_count(void);
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* Replaces the process-wide globals of the reference (src/collect#$.h:17-18,31, generateSP.h:1-6,

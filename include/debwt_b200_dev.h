@@ -26,6 +26,9 @@ int debwt_dev_extract(const void* d_words, uint64_t pos_lo, uint64_t pos_hi, con
                       uint64_t idx_base, void* d_keys, void* stream);
 /* K3: sorts n keys held in d_a using d_b as scratch; *result_in_b = 1 when the sorted keys end in d_b. */
 int debwt_dev_sort(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, void* stream);
+/* same, synchronous, with device times: whole sort and the scatter passes alone (CUDA events on `stream`) */
+int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, float* ms_total, float* ms_sweeps,
+                         int* n_sweeps, void* stream);
 /* K12: owner rank of each item = number of splitters <= (item & mask); with drop_marker, items equal to ~0
    (the "no query" marker) get owner 255 and are dropped by the partition. */
 int debwt_dev_owner_of_keys(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
