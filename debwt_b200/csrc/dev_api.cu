@@ -45,36 +45,32 @@ int debwt_dev_extract(const void* d_words, uint64_t pos_lo, uint64_t pos_hi, con
     return k_extract_range(P64(d_words), pos_lo, pos_hi, P64(d_seps), n_rec, idx_base, P64(d_keys), S(stream));
 }
 
-int debwt_dev_sort(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, void* stream) {
-    cudaStream_t st = S(stream);
-    void* ws_mem = nullptr;
-    CUDA_TRY(cudaMallocAsync(&ws_mem, sort_workspace_bytes(n, cfg), st));
+uint64_t debwt_dev_sort_workspace_bytes(uint64_t n, int cfg) { return sort_workspace_bytes(n, cfg); }
+uint64_t debwt_dev_branch_workspace_bytes(uint64_t n) { return branch_workspace_bytes(n) + 64; }
+uint64_t debwt_dev_scan_workspace_bytes(uint64_t n_words) { return scan_workspace_bytes(n_words) + 64; }
+
+int debwt_dev_sort(void* d_a, void* d_b, uint64_t n, int cfg, void* d_workspace, int* result_in_b, void* stream) {
     SortWorkspace ws;
-    sort_workspace_bind(ws, ws_mem, n, cfg);
+    sort_workspace_bind(ws, d_workspace, n, cfg);
     u64* res = nullptr;
-    int rc = radix_sort_u64(P64(d_a), P64(d_b), n, ws, st, &res);
-    cudaFreeAsync(ws_mem, st);
-    if (rc) return rc;
+    if (radix_sort_u64(P64(d_a), P64(d_b), n, ws, S(stream), &res)) return -1;
     if (result_in_b) *result_in_b = (res == P64(d_b)) ? 1 : 0;
     return 0;
 }
 
-int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, float* ms_total, float* ms_sweeps,
-                         int* n_sweeps, void* stream) {
+int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, void* d_workspace, int* result_in_b, float* ms_total,
+                         float* ms_sweeps, int* n_sweeps, void* stream) {
     cudaStream_t st = S(stream);
-    void* ws_mem = nullptr;
-    CUDA_TRY(cudaMallocAsync(&ws_mem, sort_workspace_bytes(n, cfg), st));
     SortWorkspace ws;
-    sort_workspace_bind(ws, ws_mem, n, cfg);
-    cudaEvent_t e[4];
-    for (auto& x : e) CUDA_TRY(cudaEventCreate(&x));
+    sort_workspace_bind(ws, d_workspace, n, cfg);
+    static cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (!e[0]) for (auto& x : e) CUDA_TRY(cudaEventCreate(&x));
     int sweeps = 0;
     ws.ev_sweep_begin = e[1]; ws.ev_sweep_end = e[2]; ws.sweeps_out = &sweeps;
     CUDA_TRY(cudaEventRecord(e[0], st));
     u64* res = nullptr;
     int rc = radix_sort_u64(P64(d_a), P64(d_b), n, ws, st, &res);
     CUDA_TRY(cudaEventRecord(e[3], st));
-    cudaFreeAsync(ws_mem, st);
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!rc) {
         if (ms_total) CUDA_TRY(cudaEventElapsedTime(ms_total, e[0], e[3]));
@@ -82,7 +78,6 @@ int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, int* result_
         if (n_sweeps) *n_sweeps = sweeps;
         if (result_in_b) *result_in_b = (res == P64(d_b)) ? 1 : 0;
     }
-    for (auto& x : e) cudaEventDestroy(x);
     return rc;
 }
 
@@ -96,11 +91,10 @@ int debwt_dev_owner_of_index(void* d_idx, uint64_t n, const void* d_bases, uint3
 }
 
 int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8, uint64_t n, uint32_t n_ranks,
-                        void* d_out_a, void* d_out_b, uint64_t* counts_out, void* stream) {
+                        void* d_out_a, void* d_out_b, uint64_t* counts_out, void* d_workspace, void* stream) {
     if (n_ranks == 0 || n_ranks > 16) { set_error("debwt_dev_partition: 1..16 ranks"); return -1; }
     cudaStream_t st = S(stream);
-    u64* d_counts = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_counts), 16 * 8, st));
+    u64* d_counts = P64(d_workspace);
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, 16 * 8, st));
     if (k_partition_count(P8(d_dest_u8), n, d_counts, st)) return -1;
     u64 h[16];
@@ -112,8 +106,7 @@ int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8,
     if (k_partition_scatter(P64(d_a), d_b ? P64(d_b) : nullptr, P8(d_dest_u8), n, d_counts, P64(d_out_a),
                             d_out_b ? P64(d_out_b) : nullptr, st))
         return -1;
-    CUDA_TRY(cudaFreeAsync(d_counts, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(st));     // `cur` lives on this stack frame
     return 0;
 }
 
@@ -142,17 +135,15 @@ int debwt_dev_propagate(const void* d_sorted, uint64_t n, void* d_gmask, void* s
 }
 
 int debwt_dev_branch_count(const void* d_sorted, uint64_t n, const void* d_gmask, uint64_t* n_branch, uint64_t* n_blue,
-                           void** workspace, void* stream) {
+                           void* d_workspace, void* stream) {
     cudaStream_t st = S(stream);
-    char* ws = nullptr;
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ws), branch_workspace_bytes(n) + 64));
+    char* ws = reinterpret_cast<char*>(d_workspace);
     u64* d_tot = reinterpret_cast<u64*>(ws);
-    if (k_branch_count(P64(d_sorted), n, P16(d_gmask), ws + 64, d_tot, st)) { cudaFree(ws); return -1; }
+    if (k_branch_count(P64(d_sorted), n, P16(d_gmask), ws + 64, d_tot, st)) return -1;
     u64 h[2];
     CUDA_TRY(cudaMemcpyAsync(h, d_tot, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     *n_branch = h[0]; *n_blue = h[1];
-    *workspace = ws;
     return 0;
 }
 
@@ -160,12 +151,11 @@ int debwt_dev_branch_write(const void* d_sorted, uint64_t n, const void* d_gmask
                            void* d_head_u32, void* d_blue_u32, uint64_t n_branch, uint64_t n_blue, void* stream) {
     cudaStream_t st = S(stream);
     BranchTable bt = BT(d_kmer, d_head_u32, d_blue_u32, nullptr, nullptr, 0, n_branch, n_blue);
-    int rc = k_branch_write(P64(d_sorted), n, P16(d_gmask), reinterpret_cast<char*>(workspace) + 64, bt, st);
+    if (k_branch_write(P64(d_sorted), n, P16(d_gmask), reinterpret_cast<char*>(workspace) + 64, bt, st)) return -1;
     const u32 m32 = (u32)n_blue;
-    if (!rc && cudaMemcpyAsync(P32(d_blue_u32) + n_branch, &m32, 4, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
-    cudaStreamSynchronize(st);
-    cudaFree(workspace);
-    return rc;
+    CUDA_TRY(cudaMemcpyAsync(P32(d_blue_u32) + n_branch, &m32, 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int debwt_dev_branch_index(const void* d_kmer, uint64_t n_branch, void* d_bidx_u32, int bits, void* stream) {
@@ -192,15 +182,14 @@ int debwt_dev_patch_bits_slice(void* d_mo_bits, uint64_t pos_lo, uint64_t pos_hi
     return k_patch_bits_slice(P32(d_mo_bits), pos_lo, pos_hi, P64(d_positions), m, S(stream));
 }
 
-int debwt_dev_scan_popc(const void* d_mo_bits, void* d_word_prefix, uint64_t nbw, uint64_t* total, void* stream) {
+int debwt_dev_scan_popc(const void* d_mo_bits, void* d_word_prefix, uint64_t nbw, uint64_t* total, void* d_workspace,
+                        void* stream) {
     cudaStream_t st = S(stream);
-    char* ws = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), scan_workspace_bytes(nbw) + 64, st));
+    char* ws = reinterpret_cast<char*>(d_workspace);
     u64* d_tot = reinterpret_cast<u64*>(ws);
     if (scan_exclusive_u32(P32(d_mo_bits), P32(d_word_prefix), nbw, true, ws + 64, d_tot, st)) return -1;
     u64 h = 0;
     CUDA_TRY(cudaMemcpyAsync(&h, d_tot, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaFreeAsync(ws, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     *total = h;
     return 0;

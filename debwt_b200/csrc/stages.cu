@@ -261,13 +261,14 @@ int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u6
 // =============================================================================================
 namespace {
 
+// one thread per bucket boundary: idx[t] = lower_bound(keys, t << shift).  (A per-key formulation that
+// fills the gap before each key serialises badly when a device owns a narrow key range: one thread
+// would fill half of the table.)
 __global__ void __launch_bounds__(TPB) key_index_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki) {
-    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (i > n) return;
-    const int sh = 64 - ki.bits;
-    const long long cur = (i < n) ? (long long)(k[i] >> sh) : (1ll << ki.bits);
-    const long long prev = (i > 0) ? (long long)(k[i - 1] >> sh) : -1ll;
-    for (long long t = prev + 1; t <= cur; ++t) ki.idx[t] = (u32)i;
+    const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
+    const u64 nb = 1ull << ki.bits;
+    if (t > nb) return;
+    ki.idx[t] = (t == nb) ? (u32)n : (u32)lower_bound_u64(k, 0, n, t << (64 - ki.bits));
 }
 
 __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask) {
@@ -362,12 +363,10 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
 }
 
 __global__ void __launch_bounds__(TPB) branch_index_kernel(BranchTable bt) {
-    const u64 b = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (b > bt.n_branch) return;
-    const int sh = 64 - bt.bits;
-    const long long cur = (b < bt.n_branch) ? (long long)(bt.kmer[b] >> sh) : (1ll << bt.bits);
-    const long long prev = (b > 0) ? (long long)(bt.kmer[b - 1] >> sh) : -1ll;
-    for (long long t = prev + 1; t <= cur; ++t) bt.bidx[t] = (u32)b;
+    const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
+    const u64 nb = 1ull << bt.bits;
+    if (t > nb) return;
+    bt.bidx[t] = (t == nb) ? (u32)bt.n_branch : (u32)lower_bound_u64(bt.kmer, 0, bt.n_branch, t << (64 - bt.bits));
 }
 
 __global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki,
@@ -379,7 +378,7 @@ __global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict_
 }  // namespace
 
 int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
-    key_index_kernel<<<grid_for(n + 1, TPB), TPB, 0, st>>>(sorted, n, ki);
+    key_index_kernel<<<grid_for((1ull << ki.bits) + 1, TPB), TPB, 0, st>>>(sorted, n, ki);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -448,7 +447,7 @@ int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, 
 }
 
 int k_branch_index(BranchTable bt, cudaStream_t st) {
-    branch_index_kernel<<<grid_for(bt.n_branch + 1, TPB), TPB, 0, st>>>(bt);
+    branch_index_kernel<<<grid_for((1ull << bt.bits) + 1, TPB), TPB, 0, st>>>(bt);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

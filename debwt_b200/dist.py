@@ -179,6 +179,11 @@ class CudaOps:
         binding.check(rc)
         self.launches += 1
 
+    def _bytes(self, fn, *args):
+        f = getattr(self.L, fn)
+        f.restype = ctypes.c_uint64
+        return int(f(*args))
+
     def empty(self, n, dtype=torch.int64):
         return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
 
@@ -203,14 +208,15 @@ class CudaOps:
         if n <= 1:
             return keys
         tmp = torch.empty_like(keys)
+        ws = self.empty(self._bytes("debwt_dev_sort_workspace_bytes", _u64(n), self.sort_cfg), torch.uint8)
         in_b = ctypes.c_int(0)
         if timed:
             ms, msw, nsw = ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
-            self._ck(self.L.debwt_dev_sort_timed(_p(keys), _p(tmp), _u64(n), self.sort_cfg, ctypes.byref(in_b), ctypes.byref(ms),
-                                                 ctypes.byref(msw), ctypes.byref(nsw), self._st()))
+            self._ck(self.L.debwt_dev_sort_timed(_p(keys), _p(tmp), _u64(n), self.sort_cfg, _p(ws), ctypes.byref(in_b),
+                                                 ctypes.byref(ms), ctypes.byref(msw), ctypes.byref(nsw), self._st()))
             self.sort_stats = {"n": n, "ms": ms.value, "ms_sweeps": msw.value, "sweeps": nsw.value}
         else:
-            self._ck(self.L.debwt_dev_sort(_p(keys), _p(tmp), _u64(n), self.sort_cfg, ctypes.byref(in_b), self._st()))
+            self._ck(self.L.debwt_dev_sort(_p(keys), _p(tmp), _u64(n), self.sort_cfg, _p(ws), ctypes.byref(in_b), self._st()))
         return tmp if in_b.value else keys
 
     def owner_of_keys(self, items, splitters, mask, drop_marker):
@@ -230,9 +236,10 @@ class CudaOps:
         out_a = torch.empty_like(a)
         out_b = torch.empty_like(b) if b is not None else None
         counts = (ctypes.c_uint64 * 16)()
+        ws = self.empty(32)
         self._ck(self.L.debwt_dev_partition(_p(a), _p(b) if b is not None else ctypes.c_void_p(0), _p(dest), _u64(n),
                                             ctypes.c_uint32(n_ranks), _p(out_a),
-                                            _p(out_b) if out_b is not None else ctypes.c_void_p(0), counts, self._st()))
+                                            _p(out_b) if out_b is not None else ctypes.c_void_p(0), counts, _p(ws), self._st()))
         return out_a, out_b, [int(counts[i]) for i in range(n_ranks)]
 
     def key_index(self, sorted_keys):
@@ -260,14 +267,15 @@ class CudaOps:
 
     def branch_table(self, sorted_keys, gmask):
         n = sorted_keys.numel()
-        nb, nblue, ws = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_void_p()
+        nb, nblue = ctypes.c_uint64(), ctypes.c_uint64()
         if n == 0:
             return {"kmer": self.empty(0), "head": self.empty(0, torch.int32), "blue": self.zeros(1, torch.int32), "B": 0, "M": 0}
+        ws = self.empty(self._bytes("debwt_dev_branch_workspace_bytes", _u64(n)), torch.uint8)
         self._ck(self.L.debwt_dev_branch_count(_p(sorted_keys), _u64(n), _p(gmask), ctypes.byref(nb), ctypes.byref(nblue),
-                                               ctypes.byref(ws), self._st()))
+                                               _p(ws), self._st()))
         B, M = nb.value, nblue.value
         kmer, head, blue = self.empty(B + 1), self.empty(B + 1, torch.int32), self.zeros(B + 2, torch.int32)
-        self._ck(self.L.debwt_dev_branch_write(_p(sorted_keys), _u64(n), _p(gmask), ws, _p(kmer), _p(head), _p(blue), _u64(B),
+        self._ck(self.L.debwt_dev_branch_write(_p(sorted_keys), _u64(n), _p(gmask), _p(ws), _p(kmer), _p(head), _p(blue), _u64(B),
                                                _u64(M), self._st()))
         return {"kmer": kmer[:B], "head": head[:B], "blue": blue[:B + 1], "B": B, "M": M}
 
@@ -303,7 +311,8 @@ class CudaOps:
     def scan_popc(self, mo, nbw):
         wp = self.empty(nbw + 2, torch.int32)
         total = ctypes.c_uint64()
-        self._ck(self.L.debwt_dev_scan_popc(_p(mo), _p(wp), _u64(nbw), ctypes.byref(total), self._st()))
+        ws = self.empty(self._bytes("debwt_dev_scan_workspace_bytes", _u64(nbw)), torch.uint8)
+        self._ck(self.L.debwt_dev_scan_popc(_p(mo), _p(wp), _u64(nbw), ctypes.byref(total), _p(ws), self._st()))
         return wp, total.value
 
     def emit_codes_slice(self, words, word_lo, nbw, mo, wp, code_base, codes):
@@ -502,16 +511,23 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     # 4. branch k-mer detection on the owned key range
     ki = ops.key_index(sk)
     gmask = ops.zeros(n_loc + 2, torch.int16)
+    tick('c.index')
     q = ops.out_edges_queries(sk, gmask) if n_loc else ops.empty(0)
+    tick('c.out_edges')
     dq = owner(q, 0xFFFFFFFFFFFFFFFC, True)
     qpart, _, qcounts = ops.partition(q, None, dq, G)
+    tick('c.partition')
     qrecv, _ = comm.all_to_all_v(qpart, qcounts)
+    tick('c.alltoall')
     if n_loc:
         ops.apply_in_queries(sk, ki, gmask, qrecv)
+        tick('c.apply')
         ops.heads_tails(words, d_seps, R, sk, ki, gmask)
         ops.propagate(sk, gmask)
     del q, qpart, qrecv, dq
+    tick('c.propagate')
     bt = ops.branch_table(sk, gmask)
+    tick('c.branch')
     gkmer, b_all = comm.all_gather_var(bt["kmer"])
     b_base = np.concatenate(([0], np.cumsum(b_all))).astype(np.uint64)
     m_all = comm.all_gather_scalar(bt["M"])

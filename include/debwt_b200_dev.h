@@ -24,20 +24,26 @@ int debwt_dev_pack(const void* d_ascii, uint64_t n, void* d_words, uint64_t nwor
 /* K2 on positions [pos_lo, pos_hi): key of window p in record r goes to keys[p - 32 r - idx_base]. */
 int debwt_dev_extract(const void* d_words, uint64_t pos_lo, uint64_t pos_hi, const void* d_seps, uint64_t n_rec,
                       uint64_t idx_base, void* d_keys, void* stream);
+/* Workspaces are provided by the caller (device memory, sizes in bytes from the *_workspace_bytes calls):
+   no call in this header allocates or frees device memory. */
+uint64_t debwt_dev_sort_workspace_bytes(uint64_t n, int cfg);
+uint64_t debwt_dev_branch_workspace_bytes(uint64_t n);
+uint64_t debwt_dev_scan_workspace_bytes(uint64_t n_words);
 /* K3: sorts n keys held in d_a using d_b as scratch; *result_in_b = 1 when the sorted keys end in d_b. */
-int debwt_dev_sort(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, void* stream);
+int debwt_dev_sort(void* d_a, void* d_b, uint64_t n, int cfg, void* d_workspace, int* result_in_b, void* stream);
 /* same, synchronous, with device times: whole sort and the scatter passes alone (CUDA events on `stream`) */
-int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, int* result_in_b, float* ms_total, float* ms_sweeps,
-                         int* n_sweeps, void* stream);
+int debwt_dev_sort_timed(void* d_a, void* d_b, uint64_t n, int cfg, void* d_workspace, int* result_in_b, float* ms_total,
+                         float* ms_sweeps, int* n_sweeps, void* stream);
 /* K12: owner rank of each item = number of splitters <= (item & mask); with drop_marker, items equal to ~0
    (the "no query" marker) get owner 255 and are dropped by the partition. */
 int debwt_dev_owner_of_keys(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
                             int drop_marker, void* d_dest_u8, void* stream);
 /* owner of a global table index given the n_ranks+1 ascending bases; idx is rewritten to the owner-local index */
 int debwt_dev_owner_of_index(void* d_idx, uint64_t n, const void* d_bases, uint32_t n_ranks, void* d_dest_u8, void* stream);
-/* groups a (and b when non-null) by owner; counts_out[r] = items of owner r (host array of n_ranks) */
+/* groups a (and b when non-null) by owner; counts_out[r] = items of owner r (host array of n_ranks);
+   d_workspace: 128 bytes */
 int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8, uint64_t n, uint32_t n_ranks,
-                        void* d_out_a, void* d_out_b, uint64_t* counts_out, void* stream);
+                        void* d_out_a, void* d_out_b, uint64_t* counts_out, void* d_workspace, void* stream);
 /* direct index over sorted keys */
 int debwt_dev_key_index_bits(uint64_t n);
 int debwt_dev_key_index(const void* d_sorted, uint64_t n, void* d_idx_u32, int bits, void* stream);
@@ -48,9 +54,9 @@ int debwt_dev_apply_in_queries(const void* d_sorted, uint64_t n, const void* d_i
 int debwt_dev_heads_tails(const void* d_words, const void* d_seps, uint64_t n_rec, const void* d_sorted, uint64_t n,
                           const void* d_idx_u32, int bits, void* d_gmask, void* stream);
 int debwt_dev_propagate(const void* d_sorted, uint64_t n, void* d_gmask, void* stream);
-/* K7: two calls; the first returns B, M and an opaque device workspace the second consumes and frees */
+/* K7: two calls sharing one workspace; the first returns B and M */
 int debwt_dev_branch_count(const void* d_sorted, uint64_t n, const void* d_gmask, uint64_t* n_branch, uint64_t* n_blue,
-                           void** workspace, void* stream);
+                           void* d_workspace, void* stream);
 int debwt_dev_branch_write(const void* d_sorted, uint64_t n, const void* d_gmask, void* workspace, void* d_kmer,
                            void* d_head_u32, void* d_blue_u32 /* B+1 */, uint64_t n_branch, uint64_t n_blue, void* stream);
 int debwt_dev_branch_index(const void* d_kmer, uint64_t n_branch, void* d_bidx_u32, int bits, void* stream);
@@ -68,7 +74,8 @@ int debwt_dev_flag_slice(const void* d_words, uint64_t pos_lo, uint64_t pos_hi, 
                          void* d_rec_entry, void* d_rec_index, void* d_rec_count, void* stream);
 int debwt_dev_patch_bits_slice(void* d_mo_bits, uint64_t pos_lo, uint64_t pos_hi, const void* d_positions, uint64_t m,
                                void* stream);
-int debwt_dev_scan_popc(const void* d_mo_bits, void* d_word_prefix, uint64_t nbw, uint64_t* total, void* stream);
+int debwt_dev_scan_popc(const void* d_mo_bits, void* d_word_prefix, uint64_t nbw, uint64_t* total, void* d_workspace,
+                        void* stream);
 int debwt_dev_emit_codes_slice(const void* d_words, uint64_t word_lo, uint64_t nbw, const void* d_mo_bits,
                                const void* d_word_prefix, uint64_t code_base, void* d_codes, void* stream);
 int debwt_dev_mark_sep_slice(const void* d_mo_bits, const void* d_word_prefix, uint64_t pos_lo, uint64_t pos_hi,
