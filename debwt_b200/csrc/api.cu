@@ -517,7 +517,7 @@ int debwt_build(debwt_ctx* c, int k) {
 
     // ---- K10 segmented sort ----
     u32* d_work = nullptr;
-    if (dalloc(pool, &d_work, bt.n_branch + 8)) return -1;
+    if (dalloc(pool, &d_work, 4 * bt.n_branch + 16)) return -1;
     SpView spv{d_codes, d_sep, dollar_index, n_codes};
     if (k_sort_blue(d_blue, bt, spv, d_work, st)) return -1;
     mark();                                                                     // ev7

@@ -5,9 +5,16 @@
 // codes compared 32 at a time (one u64), '#' > T and equal '#' compared through, '$' largest
 // (src/sortBlue.c:109-173).
 //
-//   * segments of <= 32 entries (the overwhelming majority): one warp per segment, rank by counting;
-//   * larger segments: one thread block per segment, same-direction bitonic network (virtual +inf
-//     padding, so no scratch), in shared memory up to 2048 entries, in place in HBM beyond that.
+// Every entry first caches the first 32 codes of its string (one u64, fetched once); almost all
+// comparisons are decided on the cached word without touching memory, the rest continue in the code
+// array from code 32 on.  Segments are binned by size:
+//   <= 32   : one warp, entries in registers, rank by counting;
+//   <= 128  : one warp, entries + cached words in shared memory, same-direction bitonic network;
+//   <= 2048 : one thread block, shared memory, same network;
+//   larger  : one thread block, in place in HBM with the cached words in a scratch array.
+// The network uses virtual +inf padding (all compare-exchanges point the same way), so no segment
+// needs scratch for padding.  Segments whose prev symbols are all equal are skipped
+// (src/sortBlue.c:192-219): any order gives the same BWT.
 #include "stages.cuh"
 
 namespace debwt {
@@ -15,6 +22,8 @@ namespace debwt {
 namespace {
 
 constexpr int TPB = 256;
+constexpr int WARPS = TPB / 32;
+constexpr int MID_SEG = 128;
 constexpr int BIG_TPB = 512;
 constexpr int SMEM_SEG = 2048;
 
@@ -26,8 +35,10 @@ __device__ __forceinline__ u32 fetch_sep(const u32* __restrict__ sep, u64 s) {
     return (lo >> sh) | (sep[i + 1] << (32 - sh));
 }
 
-// strict "string at sa < string at sb"; sa != sb
-__device__ __forceinline__ bool sp_less(const SpView& v, u64 sa, u64 sb) {
+// strict "string at sa < string at sb" starting the comparison `skip` codes in; sa != sb
+__device__ __forceinline__ bool sp_less_from(const SpView& v, u64 sa, u64 sb, u32 skip) {
+    sa += skip;
+    sb += skip;
     for (;;) {
         const u64 ca = text_window32(v.codes, sa), cb = text_window32(v.codes, sb);
         const u32 fa = fetch_sep(v.sep, sa), fb = fetch_sep(v.sep, sb);
@@ -47,100 +58,210 @@ __device__ __forceinline__ bool sp_less(const SpView& v, u64 sa, u64 sb) {
     }
 }
 
-__global__ void __launch_bounds__(TPB) sort_blue_small_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
-                                                             u32* __restrict__ big_list, u32* __restrict__ big_count) {
+// cached first word of an entry's string; `plain` = no separator code among its first 32 codes
+struct Cached {
+    u64 word;
+    bool plain;
+};
+__device__ __forceinline__ Cached cache_of(const SpView& v, u64 entry) {
+    const u64 s = entry >> 4;
+    Cached c;
+    c.word = text_window32(v.codes, s);
+    c.plain = fetch_sep(v.sep, s) == 0;
+    return c;
+}
+
+// a cached word is only trusted when both sides are free of separator codes
+__device__ __forceinline__ bool entry_less(const SpView& v, u64 ea, u64 wa, bool pa, u64 eb, u64 wb, bool pb) {
+    if (pa && pb) {
+        if (wa != wb) return wa < wb;
+        return sp_less_from(v, ea >> 4, eb >> 4, 32);
+    }
+    return sp_less_from(v, ea >> 4, eb >> 4, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// binning
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) bin_segments_kernel(BranchTable bt, u32* __restrict__ counts /*[4]*/,
+                                                          u32* __restrict__ small, u32* __restrict__ mid,
+                                                          u32* __restrict__ block, u32* __restrict__ huge) {
+    const u64 b = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (b >= bt.n_branch) return;
+    if (!(bt.kmer[b] & 2ull)) return;
+    const u32 len = bt.blue[b + 1] - bt.blue[b];
+    if (len <= 1) return;
+    if (len <= 32) small[atomicAdd(counts + 0, 1u)] = (u32)b;
+    else if (len <= MID_SEG) mid[atomicAdd(counts + 1, 1u)] = (u32)b;
+    else if (len <= SMEM_SEG) block[atomicAdd(counts + 2, 1u)] = (u32)b;
+    else huge[atomicAdd(counts + 3, 1u)] = (u32)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// <= 32: one warp, registers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) sort_small_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
+                                                        const u32* __restrict__ list, const u32* __restrict__ count) {
     const int lane = threadIdx.x & 31;
-    const u64 nwarps = (u64)gridDim.x * (TPB / 32);
-    for (u64 b = ((u64)blockIdx.x * TPB + threadIdx.x) >> 5; b < bt.n_branch; b += nwarps) {
-        if (!(bt.kmer[b] & 2ull)) continue;
+    const u32 n = *count;
+    const u32 nwarps = gridDim.x * WARPS;
+    for (u32 idx = (blockIdx.x * TPB + threadIdx.x) >> 5; idx < n; idx += nwarps) {
+        const u32 b = list[idx];
         const u32 off = bt.blue[b];
         const u32 len = bt.blue[b + 1] - off;
-        if (len <= 1) continue;
-        if (len > 32) {
-            if (lane == 0) big_list[atomicAdd(big_count, 1u)] = (u32)b;
-            continue;
-        }
-        const u64 e = (u32)lane < len ? blue[(u64)off + lane] : 0;
-        const u64 s = e >> 4;
-        // every prev symbol equal -> any order gives the same BWT (src/sortBlue.c:192-219)
+        const bool act = (u32)lane < len;
+        const u64 e = act ? blue[(u64)off + lane] : 0;
         const u32 c0 = __shfl_sync(0xffffffffu, (u32)(e & 15ull), 0);
-        if (__all_sync(0xffffffffu, (u32)lane >= len || (u32)(e & 15ull) == c0)) continue;
+        if (__all_sync(0xffffffffu, !act || (u32)(e & 15ull) == c0)) continue;
+        Cached c{0, false};
+        if (act) c = cache_of(sp, e);
         u32 rank = 0;
         for (u32 j = 0; j < len; ++j) {
             __syncwarp();
-            const u64 sj = __shfl_sync(0xffffffffu, s, j);
-            if ((u32)lane < len && j != (u32)lane && sp_less(sp, sj, s)) ++rank;
+            const u64 ej = __shfl_sync(0xffffffffu, e, j);
+            const u64 wj = __shfl_sync(0xffffffffu, c.word, j);
+            const bool pj = __shfl_sync(0xffffffffu, (int)c.plain, j);
+            if (act && j != (u32)lane && entry_less(sp, ej, wj, pj, e, c.word, c.plain)) ++rank;
         }
         __syncwarp();
-        if ((u32)lane < len) blue[(u64)off + rank] = e;
+        if (act) blue[(u64)off + rank] = e;
         __syncwarp();
     }
 }
 
-template <typename Ptr>
-__device__ __forceinline__ void cmpswap(Ptr a, u64 i, u64 l, const SpView& sp) {
-    const u64 x = a[i], y = a[l];
-    if (sp_less(sp, y >> 4, x >> 4)) { a[i] = y; a[l] = x; }
-}
-
-template <typename Ptr>
-__device__ void bitonic_same_direction(Ptr a, u64 len, const SpView& sp) {
+// ---------------------------------------------------------------------------------------------
+// same-direction bitonic network over (entry, cached word, plain flag); `nthreads` cooperating threads
+// ---------------------------------------------------------------------------------------------
+template <typename Sync>
+__device__ __forceinline__ void bitonic_cached(u64* ent, u64* wrd, u8* pln, u64 len, const SpView& sp, u32 tid, u32 nthreads,
+                                               Sync sync) {
     u64 P = 1;
     while (P < len) P <<= 1;
+    auto cmpswap = [&](u64 i, u64 l) {
+        const u64 ei = ent[i], el = ent[l], wi = wrd[i], wl = wrd[l];
+        const bool pi = pln[i], pl = pln[l];
+        if (entry_less(sp, el, wl, pl, ei, wi, pi)) {
+            ent[i] = el; ent[l] = ei; wrd[i] = wl; wrd[l] = wi; pln[i] = pl; pln[l] = pi;
+        }
+    };
     for (u64 k = 2; k <= P; k <<= 1) {
         const u64 half = k >> 1;
-        for (u64 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {      // mirror step
+        for (u64 t = tid; t < (P >> 1); t += nthreads) {                 // mirror step
             const u64 i = (t / half) * k + (t % half);
             const u64 l = i ^ (k - 1);
-            if (l < len) cmpswap(a, i, l, sp);
+            if (l < len) cmpswap(i, l);
         }
-        __syncthreads();
-        for (u64 j = k >> 2; j > 0; j >>= 1) {                          // half cleaners
-            for (u64 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        sync();
+        for (u64 j = k >> 2; j > 0; j >>= 1) {                           // half cleaners
+            for (u64 t = tid; t < (P >> 1); t += nthreads) {
                 const u64 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const u64 l = i | j;
-                if (l < len) cmpswap(a, i, l, sp);
+                if (l < len) cmpswap(i, l);
             }
-            __syncthreads();
+            sync();
         }
     }
 }
 
-__global__ void __launch_bounds__(BIG_TPB) sort_blue_big_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
-                                                               const u32* __restrict__ big_list,
-                                                               const u32* __restrict__ big_count) {
-    __shared__ u64 s_seg[SMEM_SEG];
-    const u32 nbig = *big_count;
-    for (u32 idx = blockIdx.x; idx < nbig; idx += gridDim.x) {
-        const u32 b = big_list[idx];
+// 33..128: one warp per segment, shared memory
+__global__ void __launch_bounds__(TPB) sort_mid_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
+                                                      const u32* __restrict__ list, const u32* __restrict__ count) {
+    __shared__ u64 s_ent[WARPS][MID_SEG];
+    __shared__ u64 s_wrd[WARPS][MID_SEG];
+    __shared__ u8 s_pln[WARPS][MID_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 n = *count;
+    const u32 nwarps = gridDim.x * WARPS;
+    for (u32 idx = (blockIdx.x * TPB + threadIdx.x) >> 5; idx < n; idx += nwarps) {
+        const u32 b = list[idx];
+        const u64 off = bt.blue[b];
+        const u32 len = bt.blue[b + 1] - (u32)off;
+        bool same = true;
+        const u32 c0 = (u32)(blue[off] & 15ull);
+        for (u32 t = lane; t < len; t += 32) {
+            const u64 e = blue[off + t];
+            const Cached c = cache_of(sp, e);
+            s_ent[warp][t] = e; s_wrd[warp][t] = c.word; s_pln[warp][t] = c.plain;
+            same &= (u32)(e & 15ull) == c0;
+        }
+        __syncwarp();
+        if (__all_sync(0xffffffffu, same)) continue;
+        bitonic_cached(s_ent[warp], s_wrd[warp], s_pln[warp], len, sp, lane, 32, [] { __syncwarp(); });
+        for (u32 t = lane; t < len; t += 32) blue[off + t] = s_ent[warp][t];
+        __syncwarp();
+    }
+}
+
+// 129..2048: one block per segment in shared memory; larger: in place in HBM with scratch for the cache
+__global__ void __launch_bounds__(BIG_TPB) sort_block_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
+                                                            const u32* __restrict__ list, const u32* __restrict__ count,
+                                                            u64* __restrict__ g_wrd, u8* __restrict__ g_pln, bool in_hbm) {
+    __shared__ u64 s_ent[SMEM_SEG];
+    __shared__ u64 s_wrd[SMEM_SEG];
+    __shared__ u8 s_pln[SMEM_SEG];
+    __shared__ int s_same;
+    const u32 n = *count;
+    for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const u32 b = list[idx];
         const u64 off = bt.blue[b];
         const u64 len = bt.blue[b + 1] - off;
-        u64* a = blue + off;
-        if (len <= SMEM_SEG) {
-            for (u64 t = threadIdx.x; t < len; t += blockDim.x) s_seg[t] = a[t];
-            __syncthreads();
-            bitonic_same_direction(s_seg, len, sp);
-            for (u64 t = threadIdx.x; t < len; t += blockDim.x) a[t] = s_seg[t];
-            __syncthreads();
-        } else {
-            bitonic_same_direction(a, len, sp);
+        if (threadIdx.x == 0) s_same = 1;
+        __syncthreads();
+        const u32 c0 = (u32)(blue[off] & 15ull);
+        bool same = true;
+        u64* ent = in_hbm ? blue + off : s_ent;
+        u64* wrd = in_hbm ? g_wrd + off : s_wrd;
+        u8* pln = in_hbm ? g_pln + off : s_pln;
+        for (u64 t = threadIdx.x; t < len; t += blockDim.x) {
+            const u64 e = blue[off + t];
+            const Cached c = cache_of(sp, e);
+            if (!in_hbm) ent[t] = e;
+            wrd[t] = c.word; pln[t] = c.plain;
+            same &= (u32)(e & 15ull) == c0;
         }
+        if (!same) s_same = 0;
+        __syncthreads();
+        if (!s_same) {
+            bitonic_cached(ent, wrd, pln, len, sp, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+            if (!in_hbm)
+                for (u64 t = threadIdx.x; t < len; t += blockDim.x) blue[off + t] = ent[t];
+        }
+        __syncthreads();
     }
 }
 
 }  // namespace
 
+// d_work: 8 counter words + 4 lists of n_branch entries each (u32) => 4 * n_branch + 16 words
 int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t st) {
     if (bt.n_blue == 0 || bt.n_branch == 0) return 0;
-    u32* big_count = d_work;
-    u32* big_list = d_work + 4;
-    CUDA_TRY(cudaMemsetAsync(big_count, 0, 16, st));
-    u64 blocks = (bt.n_branch + (TPB / 32) - 1) / (TPB / 32);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    sort_blue_small_kernel<<<(unsigned)blocks, TPB, 0, st>>>(blue, bt, sp, big_list, big_count);
-    CUDA_TRY(cudaGetLastError());
-    sort_blue_big_kernel<<<148 * 2, BIG_TPB, 0, st>>>(blue, bt, sp, big_list, big_count);
-    DEBWT_COUNT(2);
+    u32* counts = d_work;
+    u32* small = d_work + 8;
+    u32* mid = small + bt.n_branch;
+    u32* block = mid + bt.n_branch;
+    u32* huge = block + bt.n_branch;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, 32, st));
+    bin_segments_kernel<<<(unsigned)((bt.n_branch + TPB - 1) / TPB), TPB, 0, st>>>(bt, counts, small, mid, block, huge);
+    u32 h[4];
+    CUDA_TRY(cudaMemcpyAsync(h, counts, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int launched = 1;
+    auto blocks_for = [](u32 warps) { u32 b = (warps + WARPS - 1) / WARPS; return b > 148u * 16u ? 148u * 16u : (b ? b : 1u); };
+    if (h[0]) { sort_small_kernel<<<blocks_for(h[0]), TPB, 0, st>>>(blue, bt, sp, small, counts + 0); ++launched; }
+    if (h[1]) { sort_mid_kernel<<<blocks_for(h[1]), TPB, 0, st>>>(blue, bt, sp, mid, counts + 1); ++launched; }
+    if (h[2]) {
+        sort_block_kernel<<<h[2] < 148u * 2u ? h[2] : 148u * 2u, BIG_TPB, 0, st>>>(blue, bt, sp, block, counts + 2, nullptr, nullptr, false);
+        ++launched;
+    }
+    if (h[3]) {
+        u64* g_wrd = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_wrd), bt.n_blue * 9 + 64, st));
+        u8* g_pln = reinterpret_cast<u8*>(g_wrd + bt.n_blue);
+        sort_block_kernel<<<h[3] < 148u * 2u ? h[3] : 148u * 2u, BIG_TPB, 0, st>>>(blue, bt, sp, huge, counts + 3, g_wrd, g_pln, true);
+        CUDA_TRY(cudaFreeAsync(g_wrd, st));
+        ++launched;
+    }
+    DEBWT_COUNT(launched);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

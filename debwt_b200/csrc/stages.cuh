@@ -87,7 +87,7 @@ struct SpView {
     u64 dollar_index;   // index of the one '$' code
     u64 n_codes;        // S
 };
-int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work /* >= B+4 u32 */, cudaStream_t st);
+int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work /* >= 4 B + 16 u32 */, cudaStream_t st);
 
 // ---- K8 / K11 emission ---------------------------------------------------------------------
 // bwt: ceil(n/32) words.  spec_rows: m ascending rows of the special suffixes.

@@ -339,7 +339,7 @@ class CudaOps:
     def sort_blue(self, blue, bt, codes, sep, dollar_index, n_codes):
         if bt["M"] == 0:
             return
-        work = self.zeros(bt["B"] + 8, torch.int32)
+        work = self.zeros(4 * bt["B"] + 16, torch.int32)
         self._ck(self.L.debwt_dev_sort_blue(_p(blue), _p(bt["kmer"]), _p(bt["blue"]), _u64(bt["B"]), _u64(bt["M"]), _p(codes),
                                             _p(sep), _u64(dollar_index), _u64(n_codes), _p(work), self._st()))
 

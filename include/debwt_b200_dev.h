@@ -83,7 +83,7 @@ int debwt_dev_mark_sep_slice(const void* d_mo_bits, const void* d_word_prefix, u
                              void* stream);
 int debwt_dev_fix_records(void* d_rec_entry, uint64_t m, const void* d_mo_bits, const void* d_word_prefix, uint64_t pos_lo,
                           uint64_t code_base, void* stream);
-/* K10 */
+/* K10; d_work_u32: 4 * n_branch + 16 words */
 int debwt_dev_scatter_blue(const void* d_rec_entry, const void* d_rec_local, uint64_t m, const void* d_kmer,
                            const void* d_blue_u32, void* d_cursor_u32, uint64_t n_branch, void* d_blue, void* stream);
 int debwt_dev_sort_blue(void* d_blue, const void* d_kmer, const void* d_blue_u32, uint64_t n_branch, uint64_t n_blue,
