@@ -145,7 +145,7 @@ using namespace debwt;
 
 struct debwt_ctx {
     int device = 0;
-    int sort_cfg = 1;   // 512 threads x 16 keys per tile (fastest measured on B200, profiles/)
+    int sort_cfg = 8;   // 384 threads x 16 keys per tile, 3 CTAs/SM (fastest measured on B200, profiles/)
     cudaStream_t st = nullptr;
     DevPool pool;
     // input

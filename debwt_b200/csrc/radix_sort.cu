@@ -128,9 +128,12 @@ __device__ __forceinline__ u32 match_digit(u32 d) {
     return peers;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS>
+// PERSIST = false: one CTA per tile.  PERSIST = true: a resident CTA loops over tiles and issues the loads
+// of its next tile right after the current one has been reordered into shared memory, so the load latency
+// and the look-back wait of tile t overlap the global loads of tile t+1 (the key registers are free then).
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, const u64* __restrict__ gbase,
+onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 ntiles, const u64* __restrict__ gbase,
                 u64* __restrict__ lookback, u32* __restrict__ tile_counter, u64 epoch) {
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * ITEMS;
@@ -140,180 +143,207 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, const 
     u32* s_whist = reinterpret_cast<u32*>(s_keys + TILE);
     u32* s_binoff = s_whist + WARPS * RADIX;
     u32* s_goff = s_binoff + RADIX;
-    u32* s_scan = s_goff + RADIX;   // 33 words + tile id
+    u32* s_scan = s_goff + RADIX;   // 33 words + tile ids
     u32* s_part = s_scan + 40;      // [GROUPS][RADIX] partial digit totals
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid == 0) s_scan[34] = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += THREADS) s_whist[i] = 0;
-    __syncthreads();
-    const u32 tile = s_scan[34];
-    const u32 tile_base = tile * (u32)TILE;
-    const u32 remain = n - tile_base;
-    const int valid = remain < (u32)TILE ? (int)remain : TILE;
-
-    // ---- load, warp striped ----
-    u64 key[ITEMS];
-    const u64* src = in + tile_base + warp * (ITEMS * 32) + lane;
-    if (valid == TILE) {
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) key[j] = ld_stream(src + j * 32);
-    } else {
-        const u32 first = tile_base + warp * (ITEMS * 32) + lane;
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) key[j] = (first + j * 32 < n) ? ld_stream(src + j * 32) : ~0ull;
-    }
-
-    // ---- rank inside the warp (stable: item order = memory order); two 16-bit ranks per register ----
     u32* wh = s_whist + warp * RADIX;
-    u32 rank2[(ITEMS + 1) / 2];
     const u32 lt = lanemask_lt();
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const u32 d = digit_of<PASS>(key[j]);
-        const u32 peers = match_digit(d);
-        const u32 pre = wh[d];
-        __syncwarp();
-        const u32 below = __popc(peers & lt);
-        if (below == 0) wh[d] = pre + __popc(peers);
-        __syncwarp();
-        const u32 r = pre + below;
-        if (j & 1) rank2[j >> 1] |= r << 16; else rank2[j >> 1] = r;
-    }
-    __syncthreads();
-
-    // ---- per digit: exclusive offsets across warps (GROUPS thread groups share the warps), tile total ----
     constexpr int GROUPS = THREADS / RADIX;               // 256 -> 1, 384 -> 1, 512 -> 2, 1024 -> 4
     constexpr int WPG = WARPS / GROUPS;                   // warps per group
     static_assert(WPG * GROUPS == WARPS, "warps must divide evenly over the digit groups");
     const int dg = tid & (RADIX - 1), grp = tid >> 8;
-    u32 part = 0;
-    if (grp < GROUPS) {
+
+    u64 key[ITEMS];
+    auto load_tile = [&](u32 t) {
+        const u32 first = t * (u32)TILE + warp * (ITEMS * 32) + lane;
+        const u64* src = in + first;
+        if (t + 1 < ntiles) {
 #pragma unroll
-        for (int w = 0; w < WPG; ++w) {
-            u32* q = s_whist + (grp * WPG + w) * RADIX + dg;
-            const u32 c = *q;
-            *q = part;
-            part += c;
+            for (int j = 0; j < ITEMS; ++j) key[j] = ld_stream(src + j * 32);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) key[j] = (first + j * 32 < n) ? ld_stream(src + j * 32) : ~0ull;
         }
-        if (GROUPS > 1) s_part[grp * RADIX + dg] = part;
-    }
-    u32 count = part, before = 0;
-    if (GROUPS > 1) {
+    };
+
+    if (tid == 0) s_scan[34] = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    u32 tile = s_scan[34];
+    if (tile >= ntiles) return;
+    load_tile(tile);
+
+    for (;;) {
+        for (int i = tid; i < WARPS * RADIX; i += THREADS) s_whist[i] = 0;
+        if (PERSIST && tid == 0) s_scan[35] = atomicAdd(tile_counter, 1u);      // claim the next tile early
         __syncthreads();
-        count = 0;
-#pragma unroll
-        for (int g = 0; g < GROUPS; ++g) {
-            const u32 v = s_part[g * RADIX + dg];
-            if (g < grp) before += v;
-            count += v;
-        }
-    }
-    const u32 off = block_exclusive_scan<THREADS>(tid < RADIX ? count : 0u, nullptr, s_scan);
-    u64 vcount = count;
-    u64* lb = lookback + (u64)tile * RADIX + tid;
-    if (tid < RADIX) {
-        s_binoff[tid] = off;
-        if (tid == RADIX - 1) vcount -= (u64)(TILE - valid);   // padding keys sit at the end of the last bin
-        // publish this tile's count right away; the prefix is resolved after the shared-memory reorder
-        st_volatile(lb, (tile == 0 ? LB_INCL : LB_AGG) | epoch | vcount);
-    }
-    __syncthreads();
-    // fold the bin offset into the per-warp offsets: one shared-memory lookup per key in the reorder
-    if (grp < GROUPS) {
-        const u32 base = s_binoff[dg] + before;
-#pragma unroll
-        for (int w = 0; w < WPG; ++w) s_whist[(grp * WPG + w) * RADIX + dg] += base;
-    }
-    __syncthreads();
+        const u32 next_tile = PERSIST ? s_scan[35] : ntiles;
+        const u32 tile_base = tile * (u32)TILE;
+        const u32 remain = n - tile_base;
+        const int valid = remain < (u32)TILE ? (int)remain : TILE;
 
-    // ---- reorder through shared memory ----
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const u32 d = digit_of<PASS>(key[j]);
-        const u32 r = (j & 1) ? (rank2[j >> 1] >> 16) : (rank2[j >> 1] & 0xffffu);
-        s_keys[wh[d] + r] = key[j];
-    }
-
-    // ---- decoupled look-back (one thread per digit) ----
-    if (tid < RADIX) {
-        u64 excl = 0;
-        if (tile != 0) {
-            // walk the predecessors LB_BATCH at a time: the loads of one batch are independent, so a long
-            // run of count-only predecessors costs one memory round trip per batch instead of per tile
-            constexpr int LB_BATCH = 4;
-            u32 left = tile;                       // predecessors not yet consumed
-            const u64* p = lb - RADIX;             // nearest unconsumed predecessor
-            u32 spins = 0;
-            bool done = false;
-            while (!done) {
-                u64 v[LB_BATCH];
-#pragma unroll
-                for (int i = 0; i < LB_BATCH; ++i) v[i] = ((u32)i < left) ? ld_volatile(p - (size_t)i * RADIX) : 0;
-                int used = 0;
-#pragma unroll
-                for (int i = 0; i < LB_BATCH; ++i) {
-                    if (done || used != i) continue;                       // stop at the first unpublished entry
-                    if ((u32)i >= left) continue;
-                    const u64 x = v[i];
-                    if ((x & LB_EPOCH_MASK) != epoch || (x >> 62) == 0) continue;
-                    excl += x & LB_VALUE_MASK;
-                    used = i + 1;
-                    if ((x >> 62) == 2) done = true;
-                }
-                p -= (size_t)used * RADIX;
-                left -= used;
-                if (used == 0 && ++spins > (1u << 24)) __trap();           // never hang the device on a bug
-            }
-            st_volatile(lb, LB_INCL | epoch | (excl + vcount));
-        }
-        s_goff[tid] = (u32)(gbase[tid] + excl) - s_binoff[tid];
-    }
-    __syncthreads();
-
-    // ---- write out: consecutive threads -> consecutive addresses inside a bin ----
-    if (valid == TILE) {
+        // ---- rank inside the warp (stable: item order = memory order); two 16-bit ranks per register ----
+        u32 rank2[(ITEMS + 1) / 2];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = tid + j * THREADS;
-            const u64 k = s_keys[i];
-            out[s_goff[digit_of<PASS>(k)] + i] = k;
+            const u32 d = digit_of<PASS>(key[j]);
+            const u32 peers = match_digit(d);
+            const u32 pre = wh[d];
+            __syncwarp();
+            const u32 below = __popc(peers & lt);
+            if (below == 0) wh[d] = pre + __popc(peers);
+            __syncwarp();
+            const u32 r = pre + below;
+            if (j & 1) rank2[j >> 1] |= r << 16; else rank2[j >> 1] = r;
         }
-    } else {
-        for (u32 i = tid; i < (u32)valid; i += THREADS) {
-            const u64 k = s_keys[i];
-            out[s_goff[digit_of<PASS>(k)] + i] = k;
+        __syncthreads();
+
+        // ---- per digit: exclusive offsets across warps (GROUPS thread groups share the warps), tile total ----
+        u32 part = 0;
+        if (grp < GROUPS) {
+#pragma unroll
+            for (int w = 0; w < WPG; ++w) {
+                u32* q = s_whist + (grp * WPG + w) * RADIX + dg;
+                const u32 c = *q;
+                *q = part;
+                part += c;
+            }
+            if (GROUPS > 1) s_part[grp * RADIX + dg] = part;
         }
+        u32 count = part, before = 0;
+        if (GROUPS > 1) {
+            __syncthreads();
+            count = 0;
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                const u32 v = s_part[g * RADIX + dg];
+                if (g < grp) before += v;
+                count += v;
+            }
+        }
+        const u32 off = block_exclusive_scan<THREADS>(tid < RADIX ? count : 0u, nullptr, s_scan);
+        u64 vcount = count;
+        u64* lb = lookback + (u64)tile * RADIX + tid;
+        if (tid < RADIX) {
+            s_binoff[tid] = off;
+            if (tid == RADIX - 1) vcount -= (u64)(TILE - valid);   // padding keys sit at the end of the last bin
+            // publish this tile's count right away; the prefix is resolved after the shared-memory reorder
+            st_volatile(lb, (tile == 0 ? LB_INCL : LB_AGG) | epoch | vcount);
+        }
+        __syncthreads();
+        // fold the bin offset into the per-warp offsets: one shared-memory lookup per key in the reorder
+        if (grp < GROUPS) {
+            const u32 base = s_binoff[dg] + before;
+#pragma unroll
+            for (int w = 0; w < WPG; ++w) s_whist[(grp * WPG + w) * RADIX + dg] += base;
+        }
+        __syncthreads();
+
+        // ---- reorder through shared memory ----
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 d = digit_of<PASS>(key[j]);
+            const u32 r = (j & 1) ? (rank2[j >> 1] >> 16) : (rank2[j >> 1] & 0xffffu);
+            s_keys[wh[d] + r] = key[j];
+        }
+
+        // ---- the key registers are free: start fetching the next tile ----
+        if (PERSIST && next_tile < ntiles) load_tile(next_tile);
+
+        // ---- decoupled look-back (one thread per digit) ----
+        if (tid < RADIX) {
+            u64 excl = 0;
+            if (tile != 0) {
+                // walk the predecessors LB_BATCH at a time: the loads of one batch are independent, so a long
+                // run of count-only predecessors costs one memory round trip per batch instead of per tile
+                constexpr int LB_BATCH = 4;
+                u32 left = tile;                       // predecessors not yet consumed
+                const u64* p = lb - RADIX;             // nearest unconsumed predecessor
+                u32 spins = 0;
+                bool done = false;
+                while (!done) {
+                    u64 v[LB_BATCH];
+#pragma unroll
+                    for (int i = 0; i < LB_BATCH; ++i) v[i] = ((u32)i < left) ? ld_volatile(p - (size_t)i * RADIX) : 0;
+                    int used = 0;
+#pragma unroll
+                    for (int i = 0; i < LB_BATCH; ++i) {
+                        if (done || used != i) continue;                       // stop at the first unpublished entry
+                        if ((u32)i >= left) continue;
+                        const u64 x = v[i];
+                        if ((x & LB_EPOCH_MASK) != epoch || (x >> 62) == 0) continue;
+                        excl += x & LB_VALUE_MASK;
+                        used = i + 1;
+                        if ((x >> 62) == 2) done = true;
+                    }
+                    p -= (size_t)used * RADIX;
+                    left -= used;
+                    if (used == 0 && ++spins > (1u << 24)) __trap();           // never hang the device on a bug
+                }
+                st_volatile(lb, LB_INCL | epoch | (excl + vcount));
+            }
+            s_goff[tid] = (u32)(gbase[tid] + excl) - s_binoff[tid];
+        }
+        __syncthreads();
+
+        // ---- write out: consecutive threads -> consecutive addresses inside a bin ----
+        if (valid == TILE) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 i = tid + j * THREADS;
+                const u64 k = s_keys[i];
+                out[s_goff[digit_of<PASS>(k)] + i] = k;
+            }
+        } else {
+            for (u32 i = tid; i < (u32)valid; i += THREADS) {
+                const u64 k = s_keys[i];
+                out[s_goff[digit_of<PASS>(k)] + i] = k;
+            }
+        }
+        if (!PERSIST || next_tile >= ntiles) break;
+        tile = next_tile;
+        __syncthreads();                       // s_keys / s_goff / s_whist are reused by the next tile
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST>
 int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, cudaStream_t st) {
     using S = SweepSmem<THREADS, ITEMS>;
-    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS, PERSIST>;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_done = true;
     }
     const u64 ntiles = (n + S::TILE - 1) / S::TILE;
-    kern<<<(unsigned)ntiles, THREADS, S::bytes, st>>>(in, out, (u32)n, ws.hist + PASS * RADIX, ws.lookback,
-                                                        ws.tile_counter + PASS, (u64)(PASS + 1) << 56);
+    u64 grid = ntiles;
+    if (PERSIST) {
+        static int resident = 0;
+        if (!resident) {
+            int dev = 0, sms = 148, per_sm = MIN_BLOCKS;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, S::bytes);
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        if (grid > (u64)resident) grid = resident;
+    }
+    kern<<<(unsigned)grid, THREADS, S::bytes, st>>>(in, out, (u32)n, (u32)ntiles, ws.hist + PASS * RADIX, ws.lookback,
+                                                      ws.tile_counter + PASS, (u64)(PASS + 1) << 56);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PERSIST = false>
 int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
     switch (pass) {
-        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0>(in, out, n, ws, st);
-        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1>(in, out, n, ws, st);
-        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2>(in, out, n, ws, st);
-        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3>(in, out, n, ws, st);
-        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4>(in, out, n, ws, st);
-        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5>(in, out, n, ws, st);
-        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6>(in, out, n, ws, st);
-        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7>(in, out, n, ws, st);
+        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0, PERSIST>(in, out, n, ws, st);
+        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1, PERSIST>(in, out, n, ws, st);
+        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2, PERSIST>(in, out, n, ws, st);
+        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3, PERSIST>(in, out, n, ws, st);
+        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4, PERSIST>(in, out, n, ws, st);
+        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5, PERSIST>(in, out, n, ws, st);
+        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6, PERSIST>(in, out, n, ws, st);
+        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7, PERSIST>(in, out, n, ws, st);
     }
 }
 
@@ -326,6 +356,9 @@ int sort_config_tile(int cfg) {
         case 3: return 384 * 16;
         case 4: return 512 * 12;
         case 5: return 1024 * 8;
+        case 6: return 512 * 16;
+        case 8: return 384 * 16;
+        case 9: return 512 * 20;
         default: return 256 * 16;
     }
 }
@@ -383,6 +416,10 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
             case 3: rc = launch_sweep<384, 16, 2>(src, dst, n, p, ws, st); break;
             case 4: rc = launch_sweep<512, 12, 2>(src, dst, n, p, ws, st); break;
             case 5: rc = launch_sweep<1024, 8, 1>(src, dst, n, p, ws, st); break;
+            case 6: rc = launch_sweep<512, 16, 2, true>(src, dst, n, p, ws, st); break;
+            case 7: rc = launch_sweep<256, 16, 4>(src, dst, n, p, ws, st); break;
+            case 8: rc = launch_sweep<384, 16, 3>(src, dst, n, p, ws, st); break;
+            case 9: rc = launch_sweep<512, 20, 2>(src, dst, n, p, ws, st); break;
             default: rc = launch_sweep<256, 16, 3>(src, dst, n, p, ws, st); break;
         }
         if (rc) return rc;

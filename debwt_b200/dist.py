@@ -165,7 +165,7 @@ def _u64(v):
 class CudaOps:
     """Stage kernels of libdebwt_b200.so on torch CUDA tensors (current device, current stream)."""
 
-    def __init__(self, device: int, sort_cfg: int = 1):
+    def __init__(self, device: int, sort_cfg: int = 8):
         self.device = torch.device("cuda", device)
         self.L = _dev_lib()
         self.sort_cfg = sort_cfg

@@ -39,7 +39,7 @@ def test_pack_rejects_non_acgt():
 
 
 # ---- K3 --------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("n", [0, 1, 2, 255, 4095, 4096, 4097, 100_000, 1_000_003])
 def test_radix_sort_random(cfg, n):
     rng = np.random.default_rng(n + cfg)
