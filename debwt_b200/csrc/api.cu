@@ -396,10 +396,9 @@ int debwt_build(debwt_ctx* c, int k) {
     if (k_build_key_index(d_keys, nk, ki, st)) return -1;
     if (k_mark_edges(d_keys, nk, ki, d_gmask, st)) return -1;
     if (k_mark_heads_tails(d_text, d_seps, R, d_keys, nk, ki, d_gmask, st)) return -1;
-    if (k_propagate(d_keys, nk, d_gmask, st)) return -1;
     void* d_brws = nullptr; u64* d_tot = nullptr;
     if (pool.alloc(&d_brws, branch_workspace_bytes(nk)) || dalloc(pool, &d_tot, 4)) return -1;
-    if (k_branch_count(d_keys, nk, d_gmask, d_brws, d_tot, st)) return -1;
+    if (k_branch_count(d_keys, nk, d_gmask, true, d_brws, d_tot, st)) return -1;
     u64 h_tot[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -139,7 +139,7 @@ int debwt_dev_branch_count(const void* d_sorted, uint64_t n, const void* d_gmask
     cudaStream_t st = S(stream);
     char* ws = reinterpret_cast<char*>(d_workspace);
     u64* d_tot = reinterpret_cast<u64*>(ws);
-    if (k_branch_count(P64(d_sorted), n, P16(d_gmask), ws + 64, d_tot, st)) return -1;
+    if (k_branch_count(P64(d_sorted), n, P16(d_gmask), false, ws + 64, d_tot, st)) return -1;
     u64 h[2];
     CUDA_TRY(cudaMemcpyAsync(h, d_tot, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -148,15 +148,60 @@ __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii,
 // =============================================================================================
 // K2: (k+1)-mer extraction                   (Jellyfish count, src/kmercounting.sh:8; src/mySort.c:54-83)
 // =============================================================================================
-__global__ void __launch_bounds__(TPB) extract_kernel(const u64* __restrict__ words, u64 n,
+// A block works on TILE_POS consecutive text positions: the packed words of the tile are staged in
+// shared memory once (every window needs two of them), and the record lookup is done once per block when
+// the tile lies inside one record (the common case), so the per-position work has no dependent global loads.
+constexpr int TILE_POS = 4096;
+constexpr int TILE_WORDS = TILE_POS / 32;
+constexpr int TILE_ROWS = TILE_POS / TPB;      // positions per thread
+
+struct TileText {
+    u64 w[TILE_WORDS + 2];
+    u64 rec_first, rec_last;                   // records of the first / last position of the tile
+    u64 sep_first, start_first;                // separator and start of record rec_first
+};
+
+__device__ __forceinline__ void tile_load(TileText& t, const u64* __restrict__ words, u64 nwords_total, u64 base, u64 n,
+                                          const u64* __restrict__ seps, u64 n_rec) {
+    const u64 w0 = base >> 5;
+    for (int i = threadIdx.x; i < TILE_WORDS + 2; i += TPB) t.w[i] = (w0 + i < nwords_total) ? words[w0 + i] : ~0ull;
+    if (threadIdx.x == 0) {
+        const u64 last = (base + TILE_POS - 1 < n) ? base + TILE_POS - 1 : n - 1;
+        t.rec_first = record_of(seps, n_rec, base);
+        t.rec_last = record_of(seps, n_rec, last);
+        t.sep_first = t.rec_first < n_rec ? seps[t.rec_first] : 0;
+        t.start_first = t.rec_first ? seps[t.rec_first - 1] + 1 : 0;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ u64 tile_window(const TileText& t, u32 local) {      // 32 symbols at tile-local position
+    const u32 i = local >> 5, sft = (local & 31) * 2;
+    const u64 a = t.w[i];
+    return sft ? (a << sft) | (t.w[i + 1] >> (64 - sft)) : a;
+}
+
+__global__ void __launch_bounds__(TPB) extract_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                      const u64* __restrict__ seps, u64 n_rec,
                                                      u64* __restrict__ keys) {
-    const u64 p = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (p >= n) return;
-    const u64 r = record_of(seps, n_rec, p);
-    if (r >= n_rec) return;
-    if (p + KMER > seps[r]) return;                // window would contain the separator
-    st_stream(keys + (p - (u64)KMER * r), text_window32(words, p));
+    __shared__ TileText t;
+    const u64 base = (u64)blockIdx.x * TILE_POS;
+    tile_load(t, words, nwords_total, base, n, seps, n_rec);
+    const bool one_record = t.rec_first == t.rec_last;
+#pragma unroll
+    for (int j = 0; j < TILE_ROWS; ++j) {
+        const u32 local = j * TPB + threadIdx.x;
+        const u64 p = base + local;
+        if (p >= n) continue;
+        u64 r = t.rec_first, sep = t.sep_first;
+        if (!one_record) {
+            r = record_of(seps, n_rec, p);
+            if (r >= n_rec) continue;
+            sep = seps[r];
+        }
+        if (p + KMER > sep) continue;              // window would contain the separator
+        st_stream(keys + (p - (u64)KMER * r), tile_window(t, local));
+    }
 }
 
 // =============================================================================================
@@ -216,7 +261,7 @@ int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cud
 }
 
 int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st) {
-    extract_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(words, n, d_seps, n_rec, keys);
+    extract_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, keys);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -261,29 +306,61 @@ int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u6
 // =============================================================================================
 namespace {
 
-// one thread per bucket boundary: idx[t] = lower_bound(keys, t << shift).  (A per-key formulation that
-// fills the gap before each key serialises badly when a device owns a narrow key range: one thread
-// would fill half of the table.)
-__global__ void __launch_bounds__(TPB) key_index_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki) {
+// idx[t] = lower_bound(keys, t << shift).  Two streaming steps: every key that opens a bucket records its
+// own position (one coalesced sweep over the keys), then every bucket that stayed empty -- rare inside
+// the key range, but a whole prefix / suffix of the table when a device owns a narrow key range --
+// resolves itself with a binary search.
+__global__ void __launch_bounds__(TPB) key_index_mark_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const int sh = 64 - ki.bits;
+    const u64 cur = k[i] >> sh;
+    if (i == 0 || (k[i - 1] >> sh) != cur) ki.idx[cur] = (u32)i;
+}
+
+__global__ void __launch_bounds__(TPB) key_index_fill_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki) {
     const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
     const u64 nb = 1ull << ki.bits;
     if (t > nb) return;
-    ki.idx[t] = (t == nb) ? (u32)n : (u32)lower_bound_u64(k, 0, n, t << (64 - ki.bits));
+    if (t == nb) { ki.idx[t] = (u32)n; return; }
+    if (ki.idx[t] == 0xFFFFFFFFu) ki.idx[t] = (u32)lower_bound_u64(k, 0, n, t << (64 - ki.bits));
 }
 
+constexpr int ME_ROWS = 4;       // independent keys per thread: four search chains in flight instead of one
+
 __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask) {
-    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (i >= n) return;
-    const u64 key = k[i];
-    if (i > 0 && k[i - 1] == key) return;           // one representative per distinct (k+1)-mer
-    // out edge: k-mer = first 31 bases, next symbol = last base
-    const u64 hp = group_head(k, i);
-    atomic_or_u16(gmask, hp, 1u << (GM_OUT_SHIFT + (u32)(key & 3)));
+    const u64 base = (u64)blockIdx.x * (TPB * ME_ROWS) + threadIdx.x;
+    u64 key[ME_ROWS], lo[ME_ROWS], hi[ME_ROWS];
+    bool act[ME_ROWS];
+#pragma unroll
+    for (int j = 0; j < ME_ROWS; ++j) {
+        const u64 i = base + (u64)j * TPB;
+        act[j] = i < n;
+        key[j] = act[j] ? k[i] : 0;
+        if (act[j] && i > 0 && k[i - 1] == key[j]) act[j] = false;     // one representative per distinct (k+1)-mer
+    }
     // in edge: (k+1)-mer cX marks k-mer X with c.  Consecutive threads query ascending X (same c), so the
     // index lookups and the short searches behind them stream through memory.
-    const u64 q = key << 2;
-    const u64 hs = indexed_lower_bound(k, ki, q);
-    if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << (u32)(key >> 62));
+#pragma unroll
+    for (int j = 0; j < ME_ROWS; ++j) {
+        const u64 t = (key[j] << 2) >> (64 - ki.bits);
+        lo[j] = act[j] ? ki.idx[t] : 0;
+        hi[j] = act[j] ? ki.idx[t + 1] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < ME_ROWS; ++j) {
+        if (!act[j]) continue;
+        const u64 q = key[j] << 2;
+        const u64 hs = lower_bound_u64(k, lo[j], hi[j], q);
+        if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << (u32)(key[j] >> 62));
+    }
+    // out edge: k-mer = first 31 bases, next symbol = last base
+#pragma unroll
+    for (int j = 0; j < ME_ROWS; ++j) {
+        if (!act[j]) continue;
+        const u64 i = base + (u64)j * TPB;
+        atomic_or_u16(gmask, group_head(k, i), 1u << (GM_OUT_SHIFT + (u32)(key[j] & 3)));
+    }
 }
 
 __global__ void __launch_bounds__(TPB) mark_heads_tails_kernel(const u64* __restrict__ words, const u64* __restrict__ seps,
@@ -315,49 +392,75 @@ __global__ void __launch_bounds__(TPB) propagate_kernel(const u64* __restrict__ 
 constexpr int BR_ITEMS = 8;
 constexpr int BR_TILE = TPB * BR_ITEMS;
 
-template <bool WRITE>
-__global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, u64 n, const u16* __restrict__ gmask,
+// Both passes read the keys row by row (thread t of row j handles key base + j*TPB + t: coalesced), find
+// group heads from the left neighbour and compact the branch groups in key order with warp ballots.
+// The count pass also copies every head's mask to the other members of its group (K6's "propagate").
+template <bool WRITE, bool PROPAGATE>
+__global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, u64 n, u16* __restrict__ gmask,
                                                     u32* __restrict__ tile_nb, u32* __restrict__ tile_blue,
                                                     const u32* __restrict__ tile_nb_ex, const u32* __restrict__ tile_blue_ex,
                                                     BranchTable bt) {
-    __shared__ u32 sm[40];
-    const u64 base = (u64)blockIdx.x * BR_TILE + (u64)threadIdx.x * BR_ITEMS;
-    u32 flags[BR_ITEMS];
-    u32 size[BR_ITEMS];
-    u32 nb = 0, nblue = 0;
+    constexpr int NW = TPB / 32;
+    __shared__ u32 s_cnt[BR_ITEMS * NW + 1], s_blue[BR_ITEMS * NW + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 base = (u64)blockIdx.x * BR_TILE;
+    const u32 lt = lanemask_lt();
+    u32 flags[BR_ITEMS], size[BR_ITEMS], bal[BR_ITEMS];
 #pragma unroll
     for (int j = 0; j < BR_ITEMS; ++j) {
-        const u64 i = base + j;
+        const u64 i = base + (u64)j * TPB + threadIdx.x;
         flags[j] = 0;
         size[j] = 0;
-        if (i < n && (i == 0 || (k[i - 1] >> 2) != (k[i] >> 2))) {
-            const u32 m = gmask[i];
-            const u32 f = (gm_multi_out(m) ? 1u : 0u) | (gm_multi_in(m) ? 2u : 0u);
-            if (f) {
-                flags[j] = f | 4u;
-                ++nb;
-                if (f & 2u) { size[j] = (u32)(group_end(k, n, i) - i); nblue += size[j]; }
+        if (i < n) {
+            const u64 key = k[i];
+            const bool head = (i == 0) || ((k[i - 1] >> 2) != (key >> 2));
+            if (head) {
+                const u32 m = gmask[i];
+                const u32 f = (gm_multi_out(m) ? 1u : 0u) | (gm_multi_in(m) ? 2u : 0u);
+                if (f) {
+                    flags[j] = f | 4u;
+                    if (f & 2u) size[j] = (u32)(group_end(k, n, i) - i);
+                }
+            } else if (PROPAGATE && !WRITE) {
+                gmask[i] = gmask[group_head(k, i)];
             }
         }
-    }
-    if (!WRITE) {
-        u32 tb, tl;
-        block_exclusive_scan<TPB>(nb, &tb, sm);
-        block_exclusive_scan<TPB>(nblue, &tl, sm);
-        if (threadIdx.x == 0) { tile_nb[blockIdx.x] = tb; tile_blue[blockIdx.x] = tl; }
-    } else {
-        u64 ob = (u64)tile_nb_ex[blockIdx.x] + block_exclusive_scan<TPB>(nb, nullptr, sm);
-        u32 ol = tile_blue_ex[blockIdx.x] + block_exclusive_scan<TPB>(nblue, nullptr, sm);
+        bal[j] = __ballot_sync(0xffffffffu, flags[j] != 0);
+        u32 sz = size[j];
 #pragma unroll
-        for (int j = 0; j < BR_ITEMS; ++j) {
-            if (flags[j]) {
-                const u64 i = base + j;
-                bt.kmer[ob] = (k[i] & ~3ull) | (flags[j] & 3u);
-                bt.head[ob] = (u32)i;
-                bt.blue[ob] = ol;
-                ol += size[j];
-                ++ob;
-            }
+        for (int o = 16; o; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        if (lane == 0) { s_cnt[j * NW + warp] = __popc(bal[j]); s_blue[j * NW + warp] = sz; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // 64 partials: serial exclusive scan
+        u32 a = 0, b = 0;
+        for (int q = 0; q < BR_ITEMS * NW; ++q) {
+            const u32 ca = s_cnt[q], cb = s_blue[q];
+            s_cnt[q] = a; s_blue[q] = b;
+            a += ca; b += cb;
+        }
+        s_cnt[BR_ITEMS * NW] = a; s_blue[BR_ITEMS * NW] = b;
+        if (!WRITE) { tile_nb[blockIdx.x] = a; tile_blue[blockIdx.x] = b; }
+    }
+    if (!WRITE) return;
+    __syncthreads();
+    const u64 ob0 = tile_nb_ex[blockIdx.x];
+    const u32 ol0 = tile_blue_ex[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < BR_ITEMS; ++j) {
+        // exclusive prefix of the sizes inside the warp row
+        u32 inc = size[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (flags[j]) {
+            const u64 i = base + (u64)j * TPB + threadIdx.x;
+            const u64 ob = ob0 + s_cnt[j * NW + warp] + __popc(bal[j] & lt);
+            bt.kmer[ob] = (k[i] & ~3ull) | (flags[j] & 3u);
+            bt.head[ob] = (u32)i;
+            bt.blue[ob] = ol0 + s_blue[j * NW + warp] + (inc - size[j]);
         }
     }
 }
@@ -378,15 +481,17 @@ __global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict_
 }  // namespace
 
 int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
-    key_index_kernel<<<grid_for((1ull << ki.bits) + 1, TPB), TPB, 0, st>>>(sorted, n, ki);
-    DEBWT_COUNT(1);
+    CUDA_TRY(cudaMemsetAsync(ki.idx, 0xFF, ((1ull << ki.bits) + 1) * 4, st));
+    if (n) key_index_mark_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, ki);
+    key_index_fill_kernel<<<grid_for((1ull << ki.bits) + 1, TPB), TPB, 0, st>>>(sorted, n, ki);
+    DEBWT_COUNT(2);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t st) {
     if (n == 0) return 0;
-    mark_edges_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, ki, gmask);
+    mark_edges_kernel<<<grid_for(n, TPB * ME_ROWS), TPB, 0, st>>>(sorted, n, ki, gmask);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -427,10 +532,11 @@ size_t branch_workspace_bytes(u64 n) {
     return nt * 16 + 16 + scan_workspace_bytes(nt);
 }
 
-int k_branch_count(const u64* sorted, u64 n, const u16* gmask, void* workspace, u64* d_totals, cudaStream_t st) {
+int k_branch_count(const u64* sorted, u64 n, u16* gmask, bool propagate, void* workspace, u64* d_totals, cudaStream_t st) {
     BranchWs w = branch_ws(workspace, n);
     BranchTable none;
-    branch_kernel<false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, none);
+    if (propagate) branch_kernel<false, true><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, none);
+    else branch_kernel<false, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, none);
     DEBWT_COUNT(1);
     if (scan_exclusive_u32(w.nb, w.nb_ex, w.nt, false, w.scan_ws, d_totals, st)) return -1;
     if (scan_exclusive_u32(w.blue, w.blue_ex, w.nt, false, w.scan_ws, d_totals + 1, st)) return -1;
@@ -440,7 +546,7 @@ int k_branch_count(const u64* sorted, u64 n, const u16* gmask, void* workspace, 
 
 int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st) {
     BranchWs w = branch_ws(workspace, n);
-    branch_kernel<true><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, nullptr, nullptr, w.nb_ex, w.blue_ex, bt);
+    branch_kernel<true, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, const_cast<u16*>(gmask), nullptr, nullptr, w.nb_ex, w.blue_ex, bt);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -508,32 +614,45 @@ int k_special_insertion(const u64* sorted, u64 n, KeyIndex ki, const u64* pads, 
 // =============================================================================================
 namespace {
 
-__global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restrict__ words, u64 n,
+__global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                             const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
                                                             u32* __restrict__ mo_bits, u64* __restrict__ blue) {
-    const u64 p = (u64)blockIdx.x * TPB + threadIdx.x;     // grid covers a multiple of 32 positions
-    bool mo = false;
-    if (p < n) {
-        const u64 r = record_of(seps, n_rec, p);
-        if (r < n_rec && p + KMER <= seps[r]) {
-            const u64 x = text_window32(words, p) & ~3ull;
-            u64 b;
-            if (branch_lookup(bt, x, b)) {
-                const u32 f = (u32)(bt.kmer[b] & 3ull);
-                mo = f & 1u;
-                if (f & 2u) {
-                    const u64 start = r ? seps[r - 1] + 1 : 0;
-                    u32 prev;
-                    if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
-                    else prev = text_symbol(words, p - 1);
-                    const u32 slot = atomicAdd(bt.cursor + b, 1u);
-                    blue[(u64)bt.blue[b] + slot] = (p << 4) | prev;
+    __shared__ TileText t;
+    const u64 base = (u64)blockIdx.x * TILE_POS;
+    tile_load(t, words, nwords_total, base, n, seps, n_rec);
+    const bool one_record = t.rec_first == t.rec_last;
+#pragma unroll 4
+    for (int j = 0; j < TILE_ROWS; ++j) {
+        const u32 local = j * TPB + threadIdx.x;
+        const u64 p = base + local;
+        bool mo = false;
+        if (p < n) {
+            u64 r = t.rec_first, sep = t.sep_first, start = t.start_first;
+            bool in_text = true;
+            if (!one_record) {
+                r = record_of(seps, n_rec, p);
+                in_text = r < n_rec;
+                if (in_text) { sep = seps[r]; start = r ? seps[r - 1] + 1 : 0; }
+            }
+            if (in_text && p + KMER <= sep) {
+                const u64 x = tile_window(t, local) & ~3ull;
+                u64 b;
+                if (branch_lookup(bt, x, b)) {
+                    const u32 f = (u32)(bt.kmer[b] & 3ull);
+                    mo = f & 1u;
+                    if (f & 2u) {
+                        u32 prev;
+                        if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
+                        else prev = text_symbol(words, p - 1);
+                        const u32 slot = atomicAdd(bt.cursor + b, 1u);
+                        blue[(u64)bt.blue[b] + slot] = (p << 4) | prev;
+                    }
                 }
             }
         }
+        const u32 bal = __ballot_sync(0xffffffffu, mo);
+        if ((threadIdx.x & 31) == 0 && p < n + 32) mo_bits[p >> 5] = bal;
     }
-    const u32 bal = __ballot_sync(0xffffffffu, mo);
-    if ((threadIdx.x & 31) == 0 && p < n + 32) mo_bits[p >> 5] = bal;
 }
 
 __global__ void __launch_bounds__(TPB) patch_bits_kernel(u32* __restrict__ mo_bits, const u64* __restrict__ pos, u64 m) {
@@ -589,8 +708,7 @@ __global__ void __launch_bounds__(TPB) blue_fix_kernel(u64* __restrict__ blue, u
 
 int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, u32* mo_bits, u64* blue,
                      cudaStream_t st) {
-    const u64 npos = (n + 31) & ~31ull;
-    flag_positions_kernel<<<grid_for(npos, TPB), TPB, 0, st>>>(words, n, d_seps, n_rec, bt, mo_bits, blue);
+    flag_positions_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, bt, mo_bits, blue);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -59,7 +59,8 @@ struct BranchTable {
 };
 size_t branch_workspace_bytes(u64 n);
 // pass 1: counts (B, M) -> d_totals[0], d_totals[1]
-int k_branch_count(const u64* sorted, u64 n, const u16* gmask, void* workspace, u64* d_totals, cudaStream_t st);
+// `propagate`: also copy every group head's mask to the other members of its group (replaces k_propagate)
+int k_branch_count(const u64* sorted, u64 n, u16* gmask, bool propagate, void* workspace, u64* d_totals, cudaStream_t st);
 // pass 2: fills kmer/head/blue (arrays must be allocated from the counts)
 int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st);
 int k_branch_index(BranchTable bt, cudaStream_t st);
