@@ -328,19 +328,26 @@ __global__ void __launch_bounds__(TPB) key_index_fill_kernel(const u64* __restri
 
 constexpr int ME_ROWS = 4;       // independent keys per thread: four search chains in flight instead of one
 
+// The in-edge join sweeps the whole key array once per first base c (queries cX ascend in X inside each
+// c block).  Thread blocks are dealt round-robin over the four c blocks, so at any time the four sweeps
+// are at about the same place in the key array and three of them hit L2 instead of HBM.
 __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask) {
-    const u64 base = (u64)blockIdx.x * (TPB * ME_ROWS) + threadIdx.x;
+    const u32 c = blockIdx.x & 3u;
+    const u64 chunk = blockIdx.x >> 2;
+    const u64 cbeg = ki.idx[(u64)c << (ki.bits - 2)];
+    const u64 cend = (c == 3) ? n : (u64)ki.idx[(u64)(c + 1) << (ki.bits - 2)];
+    const u64 base = cbeg + chunk * (TPB * ME_ROWS) + threadIdx.x;
+    if (cbeg + chunk * (TPB * ME_ROWS) >= cend) return;
     u64 key[ME_ROWS], lo[ME_ROWS], hi[ME_ROWS];
     bool act[ME_ROWS];
 #pragma unroll
     for (int j = 0; j < ME_ROWS; ++j) {
         const u64 i = base + (u64)j * TPB;
-        act[j] = i < n;
+        act[j] = i < cend;
         key[j] = act[j] ? k[i] : 0;
         if (act[j] && i > 0 && k[i - 1] == key[j]) act[j] = false;     // one representative per distinct (k+1)-mer
     }
-    // in edge: (k+1)-mer cX marks k-mer X with c.  Consecutive threads query ascending X (same c), so the
-    // index lookups and the short searches behind them stream through memory.
+    // in edge: (k+1)-mer cX marks k-mer X with c
 #pragma unroll
     for (int j = 0; j < ME_ROWS; ++j) {
         const u64 t = (key[j] << 2) >> (64 - ki.bits);
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__
         if (!act[j]) continue;
         const u64 q = key[j] << 2;
         const u64 hs = lower_bound_u64(k, lo[j], hi[j], q);
-        if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << (u32)(key[j] >> 62));
+        if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << c);
     }
     // out edge: k-mer = first 31 bases, next symbol = last base
 #pragma unroll
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
     }
     if (!WRITE) return;
     __syncthreads();
+    if (s_cnt[BR_ITEMS * NW] == 0) return;        // nothing to compact in this tile
     const u64 ob0 = tile_nb_ex[blockIdx.x];
     const u32 ol0 = tile_blue_ex[blockIdx.x];
 #pragma unroll
@@ -491,7 +499,8 @@ int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
 
 int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t st) {
     if (n == 0) return 0;
-    mark_edges_kernel<<<grid_for(n, TPB * ME_ROWS), TPB, 0, st>>>(sorted, n, ki, gmask);
+    // four interleaved streams; each gets enough blocks for the largest possible c block
+    mark_edges_kernel<<<4 * (grid_for(n, TPB * ME_ROWS) + 1), TPB, 0, st>>>(sorted, n, ki, gmask);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -752,7 +761,7 @@ int k_blue_fix(u64* blue, u64 m, const u32* mo_bits, const u32* word_prefix, cud
 // =============================================================================================
 namespace {
 
-constexpr int FILL_WORDS_PER_WARP = 8;
+constexpr int FILL_WORDS_PER_WARP = 32;
 
 __global__ void __launch_bounds__(TPB) fill_case2_kernel(const u16* __restrict__ gmask, u64 n_keys, u64 n,
                                                         const u64* __restrict__ spec_rows, u64 m, u64 nwords,
@@ -760,14 +769,12 @@ __global__ void __launch_bounds__(TPB) fill_case2_kernel(const u16* __restrict__
     __shared__ u64 s_lo, s_hi;
     constexpr int WORDS_PER_BLOCK = (TPB / 32) * FILL_WORDS_PER_WARP;
     const u64 wblock = (u64)blockIdx.x * WORDS_PER_BLOCK;
-    if (threadIdx.x == 0) {
-        s_lo = lower_bound_u64(spec_rows, 0, m, wblock * 32);
-        s_hi = lower_bound_u64(spec_rows, 0, m, (wblock + WORDS_PER_BLOCK) * 32);
-    }
+    if (threadIdx.x == 0) s_lo = lower_bound_u64(spec_rows, 0, m, wblock * 32);
+    if (threadIdx.x == 32) s_hi = lower_bound_u64(spec_rows, 0, m, (wblock + WORDS_PER_BLOCK) * 32);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 lo = s_lo, hi = s_hi;
-#pragma unroll
+#pragma unroll 4
     for (int q = 0; q < FILL_WORDS_PER_WARP; ++q) {
         const u64 w = wblock + (u64)warp * FILL_WORDS_PER_WARP + q;
         if (w >= nwords) break;                       // warp-uniform
