@@ -22,12 +22,21 @@ def splitmix64(seed: int, count: int) -> np.ndarray:
 
 
 def random_codes(seed: int, n: int) -> np.ndarray:
-    """n iid-uniform base codes (0..3)."""
+    """n iid-uniform base codes (0..3); generated in chunks so that multi-Gbp sequences fit in memory."""
     nw = (n + 31) // 32
-    w = splitmix64(seed, nw)
+    out = np.empty(nw * 32, dtype=np.uint8)
     shifts = (2 * (31 - np.arange(32))).astype(np.uint64)
-    codes = ((w[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8).reshape(-1)
-    return codes[:n]
+    gamma = np.uint64(0x9E3779B97F4A7C15)
+    chunk = 1 << 22
+    with np.errstate(over="ignore"):
+        for lo in range(0, nw, chunk):
+            hi = min(nw, lo + chunk)
+            z = (np.arange(lo + 1, hi + 1, dtype=np.uint64) * gamma) + np.uint64(seed & M64)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[lo * 32:hi * 32] = ((z[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8).reshape(-1)
+    return out[:n]
 
 
 def random_bases(seed: int, n: int) -> np.ndarray:
@@ -74,14 +83,37 @@ def _mutate(seq: np.ndarray, seed: int, rate: float) -> np.ndarray:
     return out
 
 
+def _mutate_many(master: np.ndarray, seeds: np.ndarray, rate: float) -> np.ndarray:
+    """rows i = _mutate(master, seeds[i], rate), computed for all rows at once"""
+    L = master.size
+    with np.errstate(over="ignore"):
+        z = (np.arange(1, L + 1, dtype=np.uint64)[None, :] * np.uint64(0x9E3779B97F4A7C15)) + seeds.astype(np.uint64)[:, None]
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        r = z ^ (z >> np.uint64(31))
+    thr = np.uint64(int(rate * (1 << 53)))
+    hit = (r >> np.uint64(11)) < thr
+    code = np.searchsorted(_ACGT, master)
+    delta = ((r & np.uint64(0x7FF)) % np.uint64(3)).astype(np.int64) + 1
+    out = np.where(hit, _ACGT[(code[None, :] + delta) & 3], master[None, :])
+    return out.astype(np.uint8)
+
+
 def _insert_family(seq: np.ndarray, seed: int, copies: int, length: int, sub_rate: float):
     if copies <= 0 or seq.size <= length:
         return
     master = random_bases(seed, length)
-    offs = _rand_ints(seed + (1 << 33), copies, seq.size - length)
-    for i, o in enumerate(offs.tolist()):
-        el = master if sub_rate == 0.0 else _mutate(master, seed + (1 << 34) + i, sub_rate)
-        seq[o:o + length] = el
+    offs = _rand_ints(seed + (1 << 33), copies, seq.size - length).tolist()
+    batch = max(1, (1 << 24) // length)
+    for lo in range(0, copies, batch):
+        hi = min(copies, lo + batch)
+        if sub_rate == 0.0:
+            els = None
+        else:
+            els = _mutate_many(master, np.arange(lo, hi, dtype=np.uint64) + np.uint64(seed + (1 << 34)), sub_rate)
+        for i in range(lo, hi):                      # later copies overwrite earlier ones, in order
+            o = offs[i]
+            seq[o:o + length] = master if els is None else els[i - lo]
 
 
 def genome_like(n: int, seed0: int, scale: float = 1.0) -> np.ndarray:

@@ -164,6 +164,15 @@ uint64_t oracle_rle(const uint64_t *sorted, uint64_t n, uint64_t *kmers, uint64_
     return d;
 }
 
+/* Unpacks the reference's output format back into BWT symbols (0..3, 4 '#', 5 '$'): the inverse of
+   oracle_pack_bwt / src/insertCase3.c:84-95,115-131. */
+void oracle_unpack_bwt(const uint64_t *words, uint64_t n, const uint64_t *sharp, uint64_t n_sharp, uint64_t dollar, uint8_t *out)
+{
+    for (uint64_t i = 0; i < n; i++) out[i] = (uint8_t)((words[i >> 5] >> (2 * (31 - (i & 31)))) & 3);
+    for (uint64_t i = 0; i < n_sharp; i++) out[sharp[i]] = 4;
+    out[dollar] = 5;
+}
+
 /*
  * LF-walk inversion (idea of the reference's unreachable developer check, src/LFsearch.c:49-166,
  * findSeg :167-235): rebuilds T from the BWT symbols in one N-cycle.  Size independent verifier.

@@ -34,6 +34,7 @@ def lib():
         L.oracle_sort_keys.argtypes = [vp, u64]; L.oracle_sort_keys.restype = None
         L.oracle_rle.argtypes = [vp, u64, vp, vp]; L.oracle_rle.restype = u64
         L.oracle_invert_bwt.argtypes = [vp, u64, vp]; L.oracle_invert_bwt.restype = ctypes.c_int
+        L.oracle_unpack_bwt.argtypes = [vp, u64, vp, u64, u64, vp]; L.oracle_unpack_bwt.restype = None
         _LIB = L
     return _LIB
 
@@ -91,6 +92,14 @@ def rle(sorted_keys: np.ndarray):
     ct = np.empty(s.size, dtype=np.uint64)
     d = lib().oracle_rle(_p(s), s.size, _p(km), _p(ct))
     return km[:d].copy(), ct[:d].copy()
+
+
+def unpack_bwt(words: np.ndarray, n: int, sharp: np.ndarray, dollar: np.ndarray) -> np.ndarray:
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    sharp = np.ascontiguousarray(sharp, dtype=np.uint64)
+    out = np.empty(n, dtype=np.uint8)
+    lib().oracle_unpack_bwt(_p(words), n, _p(sharp), sharp.size, int(dollar[0]), _p(out))
+    return out
 
 
 def invert_bwt(bwt_sym: np.ndarray):
