@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
                                                     BranchTable bt) {
     constexpr int NW = TPB / 32;
     __shared__ u32 s_cnt[BR_ITEMS * NW + 1], s_blue[BR_ITEMS * NW + 1];
+    if (WRITE && tile_nb[blockIdx.x] == 0) return;   // the count pass found no branch group in this tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 base = (u64)blockIdx.x * BR_TILE;
     const u32 lt = lanemask_lt();
@@ -451,7 +452,6 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
     }
     if (!WRITE) return;
     __syncthreads();
-    if (s_cnt[BR_ITEMS * NW] == 0) return;        // nothing to compact in this tile
     const u64 ob0 = tile_nb_ex[blockIdx.x];
     const u32 ol0 = tile_blue_ex[blockIdx.x];
 #pragma unroll
@@ -555,7 +555,7 @@ int k_branch_count(const u64* sorted, u64 n, u16* gmask, bool propagate, void* w
 
 int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st) {
     BranchWs w = branch_ws(workspace, n);
-    branch_kernel<true, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, const_cast<u16*>(gmask), nullptr, nullptr, w.nb_ex, w.blue_ex, bt);
+    branch_kernel<true, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, const_cast<u16*>(gmask), w.nb, nullptr, w.nb_ex, w.blue_ex, bt);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
