@@ -10,8 +10,9 @@
 // array from code 32 on.  Segments are binned by size:
 //   <= 32   : one warp, entries in registers, rank by counting;
 //   <= 128  : one warp, entries + cached words in shared memory, same-direction bitonic network;
-//   <= 2048 : one thread block, shared memory, same network;
-//   larger  : one thread block, in place in HBM with the cached words in a scratch array.
+//   <= 4096 : one thread block, shared memory, same network;
+//   larger  : one thread block; every aligned 4096-entry block of the segment is staged in shared memory
+//             once per merge level, only the stages with a longer partner distance run over HBM.
 // The network uses virtual +inf padding (all compare-exchanges point the same way), so no segment
 // needs scratch for padding.  Segments whose prev symbols are all equal are skipped
 // (src/sortBlue.c:192-219): any order gives the same BWT.
@@ -25,7 +26,7 @@ constexpr int TPB = 256;
 constexpr int WARPS = TPB / 32;
 constexpr int MID_SEG = 128;
 constexpr int BIG_TPB = 512;
-constexpr int SMEM_SEG = 2048;
+constexpr int SMEM_SEG = 4096;     // == CHUNK: largest segment sorted entirely in shared memory
 
 __device__ __forceinline__ u32 fetch_sep(const u32* __restrict__ sep, u64 s) {
     const u64 i = s >> 5;
@@ -192,13 +193,39 @@ __global__ void __launch_bounds__(TPB) sort_mid_kernel(u64* __restrict__ blue, B
     }
 }
 
-// 129..2048: one block per segment in shared memory; larger: in place in HBM with scratch for the cache
+// One network stage over global arrays (mirror step when `mirror`, half cleaner otherwise)
+__device__ __forceinline__ void global_stage(u64* ent, u64* wrd, u8* pln, u64 len, u64 P, u64 k, u64 j, bool mirror,
+                                             const SpView& sp) {
+    const u64 half = k >> 1;
+    for (u64 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        u64 i, l;
+        if (mirror) { i = (t / half) * k + (t % half); l = i ^ (k - 1); }
+        else { i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); l = i | j; }
+        if (l < len) {
+            const u64 ei = ent[i], el = ent[l], wi = wrd[i], wl = wrd[l];
+            const bool pi = pln[i], pl = pln[l];
+            if (entry_less(sp, el, wl, pl, ei, wi, pi)) {
+                ent[i] = el; ent[l] = ei; wrd[i] = wl; wrd[l] = wi; pln[i] = pl; pln[l] = pi;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// 129..CHUNK entries: one block, everything in shared memory.  Larger segments: the network stages whose
+// partner distance is below CHUNK/2 touch only one aligned CHUNK-sized block, so each block of the
+// segment is loaded into shared memory once per merge level and finishes there; only the few stages
+// with a longer partner distance run over HBM (20 instead of 136 for a 64 K segment).
+constexpr int CHUNK = 4096;
+constexpr size_t kChunkSmem = (size_t)CHUNK * 17;
+
 __global__ void __launch_bounds__(BIG_TPB) sort_block_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
                                                             const u32* __restrict__ list, const u32* __restrict__ count,
                                                             u64* __restrict__ g_wrd, u8* __restrict__ g_pln, bool in_hbm) {
-    __shared__ u64 s_ent[SMEM_SEG];
-    __shared__ u64 s_wrd[SMEM_SEG];
-    __shared__ u8 s_pln[SMEM_SEG];
+    extern __shared__ __align__(16) unsigned char blk_smem[];
+    u64* s_ent = reinterpret_cast<u64*>(blk_smem);
+    u64* s_wrd = s_ent + CHUNK;
+    u8* s_pln = reinterpret_cast<u8*>(s_wrd + CHUNK);
     __shared__ int s_same;
     const u32 n = *count;
     for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
@@ -209,24 +236,65 @@ __global__ void __launch_bounds__(BIG_TPB) sort_block_kernel(u64* __restrict__ b
         __syncthreads();
         const u32 c0 = (u32)(blue[off] & 15ull);
         bool same = true;
-        u64* ent = in_hbm ? blue + off : s_ent;
+        u64* ent = blue + off;
         u64* wrd = in_hbm ? g_wrd + off : s_wrd;
         u8* pln = in_hbm ? g_pln + off : s_pln;
         for (u64 t = threadIdx.x; t < len; t += blockDim.x) {
-            const u64 e = blue[off + t];
+            const u64 e = ent[t];
             const Cached c = cache_of(sp, e);
-            if (!in_hbm) ent[t] = e;
+            if (!in_hbm) s_ent[t] = e;
             wrd[t] = c.word; pln[t] = c.plain;
             same &= (u32)(e & 15ull) == c0;
         }
         if (!same) s_same = 0;
         __syncthreads();
-        if (!s_same) {
-            bitonic_cached(ent, wrd, pln, len, sp, threadIdx.x, blockDim.x, [] { __syncthreads(); });
-            if (!in_hbm)
-                for (u64 t = threadIdx.x; t < len; t += blockDim.x) blue[off + t] = ent[t];
+        if (s_same) continue;
+        if (!in_hbm) {
+            bitonic_cached(s_ent, s_wrd, s_pln, len, sp, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+            for (u64 t = threadIdx.x; t < len; t += blockDim.x) ent[t] = s_ent[t];
+            __syncthreads();
+            continue;
         }
-        __syncthreads();
+        u64 P = 1;
+        while (P < len) P <<= 1;
+        // level 0: sort every aligned CHUNK block in shared memory; later levels: long stages over HBM, then
+        // the stages with partner distance < CHUNK/2 block by block in shared memory
+        for (u64 k = CHUNK; k <= P; k <<= 1) {
+            if (k > CHUNK) {
+                global_stage(ent, wrd, pln, len, P, k, 0, true, sp);
+                for (u64 j = k >> 2; j >= CHUNK; j >>= 1) global_stage(ent, wrd, pln, len, P, k, j, false, sp);
+            }
+            for (u64 c0b = 0; c0b < len; c0b += CHUNK) {
+                const u64 clen = (len - c0b < CHUNK) ? len - c0b : CHUNK;
+                for (u64 t = threadIdx.x; t < clen; t += blockDim.x) {
+                    s_ent[t] = ent[c0b + t]; s_wrd[t] = wrd[c0b + t]; s_pln[t] = pln[c0b + t];
+                }
+                __syncthreads();
+                if (k == CHUNK) {
+                    bitonic_cached(s_ent, s_wrd, s_pln, clen, sp, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+                } else {
+                    // half cleaners j = CHUNK/2 .. 1 of merge level k, restricted to this block
+                    for (u64 j = CHUNK >> 1; j > 0; j >>= 1) {
+                        for (u64 t = threadIdx.x; t < (CHUNK >> 1); t += blockDim.x) {
+                            const u64 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const u64 l = i | j;
+                            if (l < clen) {
+                                const u64 ei = s_ent[i], el = s_ent[l], wi = s_wrd[i], wl = s_wrd[l];
+                                const bool pi = s_pln[i], pl = s_pln[l];
+                                if (entry_less(sp, el, wl, pl, ei, wi, pi)) {
+                                    s_ent[i] = el; s_ent[l] = ei; s_wrd[i] = wl; s_wrd[l] = wi; s_pln[i] = pl; s_pln[l] = pi;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (u64 t = threadIdx.x; t < clen; t += blockDim.x) {
+                    ent[c0b + t] = s_ent[t]; wrd[c0b + t] = s_wrd[t]; pln[c0b + t] = s_pln[t];
+                }
+                __syncthreads();
+            }
+        }
     }
 }
 
@@ -249,15 +317,20 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
     auto blocks_for = [](u32 warps) { u32 b = (warps + WARPS - 1) / WARPS; return b > 148u * 16u ? 148u * 16u : (b ? b : 1u); };
     if (h[0]) { sort_small_kernel<<<blocks_for(h[0]), TPB, 0, st>>>(blue, bt, sp, small, counts + 0); ++launched; }
     if (h[1]) { sort_mid_kernel<<<blocks_for(h[1]), TPB, 0, st>>>(blue, bt, sp, mid, counts + 1); ++launched; }
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
+        attr_done = true;
+    }
     if (h[2]) {
-        sort_block_kernel<<<h[2] < 148u * 2u ? h[2] : 148u * 2u, BIG_TPB, 0, st>>>(blue, bt, sp, block, counts + 2, nullptr, nullptr, false);
+        sort_block_kernel<<<h[2] < 148u * 3u ? h[2] : 148u * 3u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, block, counts + 2, nullptr, nullptr, false);
         ++launched;
     }
     if (h[3]) {
         u64* g_wrd = nullptr;
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_wrd), bt.n_blue * 9 + 64, st));
         u8* g_pln = reinterpret_cast<u8*>(g_wrd + bt.n_blue);
-        sort_block_kernel<<<h[3] < 148u * 2u ? h[3] : 148u * 2u, BIG_TPB, 0, st>>>(blue, bt, sp, huge, counts + 3, g_wrd, g_pln, true);
+        sort_block_kernel<<<h[3] < 148u * 3u ? h[3] : 148u * 3u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, huge, counts + 3, g_wrd, g_pln, true);
         CUDA_TRY(cudaFreeAsync(g_wrd, st));
         ++launched;
     }

@@ -192,6 +192,27 @@ def test_bwt_many_short_records(n_rec):
     assert all((a == b).all() for a, b in zip(want, got))
 
 
+@pytest.mark.parametrize("copies,el_len,muts", [(6000, 150, 4), (20000, 90, 3)])
+def test_bwt_huge_segments_vs_oracle(copies, el_len, muts):
+    # segments beyond one shared-memory block (4096 entries): the multi-level chunked network over HBM
+    rng = np.random.default_rng(copies)
+    master = synth.random_bases(99, el_len)
+    parts = []
+    for c in range(copies):
+        el = master.copy()
+        idx = rng.integers(0, el.size, size=muts)
+        el[idx] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=muts)]
+        parts.append(el)
+    recs = [np.concatenate(parts[:copies // 2]), np.concatenate(parts[copies // 2:])]
+    sym, _ = st.text_from_records(as_bytes_records(recs))
+    want = coracle.bwt(sym)
+    with api.BwtBuilder() as b:
+        b.set_records(recs)
+        b.build()
+        got = b.result()
+    assert all((a == b_).all() for a, b_ in zip(want, got))
+
+
 def test_bwt_errors():
     with pytest.raises(DebwtError):
         api.build_bwt(["ACGT" * 8])                 # 32 bp: "Length <= 32!" (src/collect#$.c:41-45)
