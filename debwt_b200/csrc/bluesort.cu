@@ -10,9 +10,10 @@
 // array from code 32 on.  Segments are binned by size:
 //   <= 32   : one warp, entries in registers, rank by counting;
 //   <= 128  : one warp, entries + cached words in shared memory, same-direction bitonic network;
-//   <= 4096 : one thread block, shared memory, same network;
-//   larger  : one thread block; every aligned 4096-entry block of the segment is staged in shared memory
-//             once per merge level, only the stages with a longer partner distance run over HBM.
+//   <= 4096 : one thread block, shared memory, round-based refinement: one cheap network per 32 codes on
+//             (tie group, code word) keys, so long common prefixes are walked once per entry, not per comparison;
+//   larger  : the same rounds over HBM; every aligned 4096-entry block of the segment is staged in shared
+//             memory once per merge level, only the stages with a longer partner distance run over HBM.
 // The network uses virtual +inf padding (all compare-exchanges point the same way), so no segment
 // needs scratch for padding.  Segments whose prev symbols are all equal are skipped
 // (src/sortBlue.c:192-219): any order gives the same BWT.
@@ -193,108 +194,241 @@ __global__ void __launch_bounds__(TPB) sort_mid_kernel(u64* __restrict__ blue, B
     }
 }
 
-// One network stage over global arrays (mirror step when `mirror`, half cleaner otherwise)
-__device__ __forceinline__ void global_stage(u64* ent, u64* wrd, u8* pln, u64 len, u64 P, u64 k, u64 j, bool mirror,
-                                             const SpView& sp) {
-    const u64 half = k >> 1;
-    for (u64 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-        u64 i, l;
-        if (mirror) { i = (t / half) * k + (t % half); l = i ^ (k - 1); }
-        else { i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); l = i | j; }
-        if (l < len) {
-            const u64 ei = ent[i], el = ent[l], wi = wrd[i], wl = wrd[l];
-            const bool pi = pln[i], pl = pln[l];
-            if (entry_less(sp, el, wl, pl, ei, wi, pi)) {
-                ent[i] = el; ent[l] = ei; wrd[i] = wl; wrd[l] = wi; pln[i] = pl; pln[l] = pi;
-            }
-        }
+// ---------------------------------------------------------------------------------------------
+// > 128 entries: round-based refinement.  Round r sorts the segment by (tie group, 32 codes at depth 32 r):
+// the comparisons of a round touch no memory beyond the staged arrays (one code word is fetched per
+// entry per round), so near-identical suffixes -- repeat families whose copies agree for hundreds of
+// codes -- cost one cheap network per 32 codes instead of a deep string walk inside every comparison.
+// A tie group is a run of entries that agreed on every word so far; it keeps its place, is refined by the
+// next word, and is finished as soon as it is a singleton or all of its prev symbols agree
+// (src/sortBlue.c:192-219).  A word that contains a separator code ('#'/'$', at most R in the whole code
+// string) cannot be compared as an integer: such a segment falls back to the comparator network.
+// ---------------------------------------------------------------------------------------------
+constexpr int CHUNK = 4096;                              // entries staged in shared memory at a time
+constexpr size_t kChunkSmem = (size_t)CHUNK * 20;        // entry 8 + key 8 + tag 4 bytes
+
+struct SegArrays {
+    u64* ent;      // entries
+    u64* key;      // current code word (or cached first word for the comparator fallback)
+    u32* tag;      // tie group id (position of the group's first entry) / plain flag for the fallback
+};
+
+struct LessGroupKey {
+    __device__ __forceinline__ bool operator()(u64, u64 ka, u32 ta, u64, u64 kb, u32 tb) const {
+        return ta != tb ? ta < tb : ka < kb;
     }
-    __syncthreads();
+};
+struct LessCached {
+    SpView sp;
+    __device__ __forceinline__ bool operator()(u64 ea, u64 ka, u32 ta, u64 eb, u64 kb, u32 tb) const {
+        return entry_less(sp, ea, ka, ta != 0, eb, kb, tb != 0);
+    }
+};
+
+template <typename Less>
+__device__ __forceinline__ void cmpswap3(const SegArrays& a, u32 i, u32 l, const Less& less) {
+    const u64 ei = a.ent[i], el = a.ent[l], ki = a.key[i], kl = a.key[l];
+    const u32 ti = a.tag[i], tl = a.tag[l];
+    if (less(el, kl, tl, ei, ki, ti)) {
+        a.ent[i] = el; a.ent[l] = ei; a.key[i] = kl; a.key[l] = ki; a.tag[i] = tl; a.tag[l] = ti;
+    }
 }
 
-// 129..CHUNK entries: one block, everything in shared memory.  Larger segments: the network stages whose
-// partner distance is below CHUNK/2 touch only one aligned CHUNK-sized block, so each block of the
-// segment is loaded into shared memory once per merge level and finishes there; only the few stages
-// with a longer partner distance run over HBM (20 instead of 136 for a 64 K segment).
-constexpr int CHUNK = 4096;
-constexpr size_t kChunkSmem = (size_t)CHUNK * 17;
+// all stages of the network whose partner distance is <= span/2, on `len` entries held in `a`
+// (span = power of two >= len for a full sort, or CHUNK for the tail stages of a longer merge level)
+template <typename Less>
+__device__ __forceinline__ void net_local(const SegArrays& a, u32 len, u32 k_first, u32 k_last, bool tail_only, const Less& less) {
+    for (u32 k = k_first; k <= k_last; k <<= 1) {
+        const u32 half = k >> 1;
+        if (!tail_only) {
+            for (u32 t = threadIdx.x; t < (k_last >> 1); t += blockDim.x) {               // mirror step
+                const u32 i = ((t & ~(half - 1)) << 1) | (t & (half - 1));
+                const u32 l = i ^ (k - 1);
+                if (l < len) cmpswap3(a, i, l, less);
+            }
+            __syncthreads();
+        }
+        for (u32 j = tail_only ? half : (k >> 2); j > 0; j >>= 1) {                       // half cleaners
+            for (u32 t = threadIdx.x; t < (k_last >> 1); t += blockDim.x) {
+                const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const u32 l = i | j;
+                if (l < len) cmpswap3(a, i, l, less);
+            }
+            __syncthreads();
+        }
+        if (tail_only) break;
+    }
+}
+
+__device__ __forceinline__ u32 pow2_at_least(u32 n) {
+    u32 p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// full network over `len` entries in `g` (HBM when len > CHUNK), staging through `s`
+template <typename Less>
+__device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool in_smem, const Less& less) {
+    if (in_smem) {                                  // the segment already sits in `s`
+        net_local(s, len, 2, pow2_at_least(len), false, less);
+        return;
+    }
+    const u32 P = pow2_at_least(len);
+    for (u32 k = CHUNK; k <= P; k <<= 1) {
+        if (k > CHUNK) {                            // stages with partner distance >= CHUNK run over HBM
+            const u32 half = k >> 1;
+            for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const u32 i = ((t & ~(half - 1)) << 1) | (t & (half - 1));
+                const u32 l = i ^ (k - 1);
+                if (l < len) cmpswap3(g, i, l, less);
+            }
+            __syncthreads();
+            for (u32 j = k >> 2; j >= (u32)CHUNK; j >>= 1) {
+                for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                    const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const u32 l = i | j;
+                    if (l < len) cmpswap3(g, i, l, less);
+                }
+                __syncthreads();
+            }
+        }
+        for (u32 c0 = 0; c0 < len; c0 += CHUNK) {   // the remaining stages block by block in shared memory
+            const u32 clen = (len - c0 < (u32)CHUNK) ? len - c0 : (u32)CHUNK;
+            for (u32 t = threadIdx.x; t < clen; t += blockDim.x) {
+                s.ent[t] = g.ent[c0 + t]; s.key[t] = g.key[c0 + t]; s.tag[t] = g.tag[c0 + t];
+            }
+            __syncthreads();
+            if (k == (u32)CHUNK) net_local(s, clen, 2, pow2_at_least(clen), false, less);
+            else net_local(s, clen, CHUNK, CHUNK, true, less);
+            for (u32 t = threadIdx.x; t < clen; t += blockDim.x) {
+                g.ent[c0 + t] = s.ent[t]; g.key[c0 + t] = s.key[t]; g.tag[c0 + t] = s.tag[t];
+            }
+            __syncthreads();
+        }
+    }
+}
 
 __global__ void __launch_bounds__(BIG_TPB) sort_block_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
                                                             const u32* __restrict__ list, const u32* __restrict__ count,
-                                                            u64* __restrict__ g_wrd, u8* __restrict__ g_pln, bool in_hbm) {
+                                                            u64* __restrict__ g_key, u32* __restrict__ g_tag, bool in_hbm) {
     extern __shared__ __align__(16) unsigned char blk_smem[];
-    u64* s_ent = reinterpret_cast<u64*>(blk_smem);
-    u64* s_wrd = s_ent + CHUNK;
-    u8* s_pln = reinterpret_cast<u8*>(s_wrd + CHUNK);
-    __shared__ int s_same;
+    SegArrays s;
+    s.ent = reinterpret_cast<u64*>(blk_smem);
+    s.key = s.ent + CHUNK;
+    s.tag = reinterpret_cast<u32*>(s.key + CHUNK);
+    __shared__ int s_flag[3];                      // [0] work left, [1] separator word seen, [2] scratch
     const u32 n = *count;
     for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
         const u32 b = list[idx];
         const u64 off = bt.blue[b];
-        const u64 len = bt.blue[b + 1] - off;
-        if (threadIdx.x == 0) s_same = 1;
-        __syncthreads();
-        const u32 c0 = (u32)(blue[off] & 15ull);
-        bool same = true;
-        u64* ent = blue + off;
-        u64* wrd = in_hbm ? g_wrd + off : s_wrd;
-        u8* pln = in_hbm ? g_pln + off : s_pln;
-        for (u64 t = threadIdx.x; t < len; t += blockDim.x) {
-            const u64 e = ent[t];
-            const Cached c = cache_of(sp, e);
-            if (!in_hbm) s_ent[t] = e;
-            wrd[t] = c.word; pln[t] = c.plain;
-            same &= (u32)(e & 15ull) == c0;
-        }
-        if (!same) s_same = 0;
-        __syncthreads();
-        if (s_same) continue;
+        const u32 len = (u32)(bt.blue[b + 1] - off);
+        SegArrays g;
+        g.ent = blue + off;
+        g.key = in_hbm ? g_key + off : s.key;
+        g.tag = in_hbm ? g_tag + off : s.tag;
+        const SegArrays& w = in_hbm ? g : s;       // where the segment lives during the rounds
         if (!in_hbm) {
-            bitonic_cached(s_ent, s_wrd, s_pln, len, sp, threadIdx.x, blockDim.x, [] { __syncthreads(); });
-            for (u64 t = threadIdx.x; t < len; t += blockDim.x) ent[t] = s_ent[t];
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) s.ent[t] = g.ent[t];
+        }
+        for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = 0;      // one tie group
+        __syncthreads();
+        bool fallback = false;
+        for (u32 depth = 0;; depth += 32) {
+            // fetch the code word at this depth for every entry that still sits in a tie group
+            if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[1] = 0; }
             __syncthreads();
-            continue;
-        }
-        u64 P = 1;
-        while (P < len) P <<= 1;
-        // level 0: sort every aligned CHUNK block in shared memory; later levels: long stages over HBM, then
-        // the stages with partner distance < CHUNK/2 block by block in shared memory
-        for (u64 k = CHUNK; k <= P; k <<= 1) {
-            if (k > CHUNK) {
-                global_stage(ent, wrd, pln, len, P, k, 0, true, sp);
-                for (u64 j = k >> 2; j >= CHUNK; j >>= 1) global_stage(ent, wrd, pln, len, P, k, j, false, sp);
-            }
-            for (u64 c0b = 0; c0b < len; c0b += CHUNK) {
-                const u64 clen = (len - c0b < CHUNK) ? len - c0b : CHUNK;
-                for (u64 t = threadIdx.x; t < clen; t += blockDim.x) {
-                    s_ent[t] = ent[c0b + t]; s_wrd[t] = wrd[c0b + t]; s_pln[t] = pln[c0b + t];
-                }
-                __syncthreads();
-                if (k == CHUNK) {
-                    bitonic_cached(s_ent, s_wrd, s_pln, clen, sp, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+                const u32 gid = w.tag[t];
+                const bool tied = (t + 1 < len && w.tag[t + 1] == gid) || (t > 0 && w.tag[t - 1] == gid);
+                if (tied) {
+                    const u64 sidx = (w.ent[t] >> 4) + depth;
+                    w.key[t] = text_window32(sp.codes, sidx);
+                    if (fetch_sep(sp.sep, sidx)) s_flag[1] = 1;
+                    if (sidx >= sp.n_codes) s_flag[1] = 1;                      // unreachable; never walk off the code string
                 } else {
-                    // half cleaners j = CHUNK/2 .. 1 of merge level k, restricted to this block
-                    for (u64 j = CHUNK >> 1; j > 0; j >>= 1) {
-                        for (u64 t = threadIdx.x; t < (CHUNK >> 1); t += blockDim.x) {
-                            const u64 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                            const u64 l = i | j;
-                            if (l < clen) {
-                                const u64 ei = s_ent[i], el = s_ent[l], wi = s_wrd[i], wl = s_wrd[l];
-                                const bool pi = s_pln[i], pl = s_pln[l];
-                                if (entry_less(sp, el, wl, pl, ei, wi, pi)) {
-                                    s_ent[i] = el; s_ent[l] = ei; s_wrd[i] = wl; s_wrd[l] = wi; s_pln[i] = pl; s_pln[l] = pi;
-                                }
-                            }
-                        }
-                        __syncthreads();
-                    }
+                    w.key[t] = 0;
                 }
-                for (u64 t = threadIdx.x; t < clen; t += blockDim.x) {
-                    ent[c0b + t] = s_ent[t]; wrd[c0b + t] = s_wrd[t]; pln[c0b + t] = s_pln[t];
+            }
+            __syncthreads();
+            if (s_flag[1]) { fallback = true; break; }
+            net_sort(g, s, len, !in_hbm, LessGroupKey());
+            // renumber: tag = index of the run's first entry (keeps every group where it is).
+            // (1) mark run heads in the top bit of the tag (neighbours compare the low 31 bits only)
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+                const bool head = t == 0 || ((w.tag[t] ^ w.tag[t - 1]) & 0x7fffffffu) || w.key[t] != w.key[t - 1];
+                if (head) w.tag[t] |= 0x80000000u;
+            }
+            __syncthreads();
+            // (2) inclusive max-scan of "own index if head else 0" (Hillis-Steele, ping-pong between the two
+            //     32-bit halves of the key words, which are free until the next fetch)
+            u32* k32 = reinterpret_cast<u32*>(w.key);
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) k32[2 * t] = (w.tag[t] & 0x80000000u) ? t : 0u;
+            __syncthreads();
+            u32 ph = 0;
+            for (u32 d = 1; d < len; d <<= 1) {
+                for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+                    u32 v = k32[2 * t + ph];
+                    if (t >= d) { const u32 o = k32[2 * (t - d) + ph]; v = o > v ? o : v; }
+                    k32[2 * t + (ph ^ 1u)] = v;
                 }
                 __syncthreads();
+                ph ^= 1u;
+            }
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = k32[2 * t + ph];
+            if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[2] = 0; }
+            __syncthreads();
+            // a tie group still needs work while it holds two different prev symbols; big ones go another
+            // round, small ones (<= 32 entries) are finished below with direct string comparisons
+            for (u32 t = threadIdx.x + 1; t < len; t += blockDim.x) {
+                const u32 gid = w.tag[t];
+                if (gid == w.tag[t - 1] && ((w.ent[t] ^ w.ent[t - 1]) & 15ull)) {
+                    s_flag[0] = 1;
+                    if (gid + 32 < len && w.tag[gid + 32] == gid) s_flag[2] = 1;
+                }
+            }
+            __syncthreads();
+            const int work_left = s_flag[0], big_left = s_flag[2];
+            __syncthreads();                       // everyone has read the flags before the next round resets them
+            if (!work_left) break;
+            if (!big_left) {
+                // every unresolved group fits a warp: rank by counting, comparing from the first unseen code on
+                const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                for (u32 h = wid; h < len; h += nw) {
+                    if (w.tag[h] != h) continue;                                   // warp-uniform
+                    const bool mem = h + lane < len && w.tag[h + lane] == h;
+                    const u32 size = __popc(__ballot_sync(0xffffffffu, mem));
+                    if (size < 2) continue;
+                    const u64 e = mem ? w.ent[h + lane] : 0;
+                    const u32 c0 = __shfl_sync(0xffffffffu, (u32)(e & 15ull), 0);
+                    if (__all_sync(0xffffffffu, !mem || (u32)(e & 15ull) == c0)) continue;
+                    u32 rank = 0;
+                    for (u32 j = 0; j < size; ++j) {
+                        __syncwarp();
+                        const u64 ej = __shfl_sync(0xffffffffu, e, j);
+                        if (mem && j != lane && sp_less_from(sp, ej >> 4, e >> 4, depth + 32)) ++rank;
+                    }
+                    __syncwarp();
+                    if (mem) w.ent[h + rank] = e;
+                    __syncwarp();
+                }
+                __syncthreads();
+                break;
             }
         }
+        if (fallback) {
+            // comparator network from scratch: cached first word + plain flag, deep compares through '#'
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+                const Cached c = cache_of(sp, w.ent[t]);
+                w.key[t] = c.word; w.tag[t] = c.plain ? 1u : 0u;
+            }
+            __syncthreads();
+            LessCached lc{sp};
+            net_sort(g, s, len, !in_hbm, lc);
+        }
+        if (!in_hbm) {
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) g.ent[t] = s.ent[t];
+        }
+        __syncthreads();
     }
 }
 
@@ -323,15 +457,15 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
         attr_done = true;
     }
     if (h[2]) {
-        sort_block_kernel<<<h[2] < 148u * 3u ? h[2] : 148u * 3u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, block, counts + 2, nullptr, nullptr, false);
+        sort_block_kernel<<<h[2] < 148u * 2u ? h[2] : 148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, block, counts + 2, nullptr, nullptr, false);
         ++launched;
     }
     if (h[3]) {
-        u64* g_wrd = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_wrd), bt.n_blue * 9 + 64, st));
-        u8* g_pln = reinterpret_cast<u8*>(g_wrd + bt.n_blue);
-        sort_block_kernel<<<h[3] < 148u * 3u ? h[3] : 148u * 3u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, huge, counts + 3, g_wrd, g_pln, true);
-        CUDA_TRY(cudaFreeAsync(g_wrd, st));
+        u64* g_key = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_key), bt.n_blue * 12 + 64, st));
+        u32* g_tag = reinterpret_cast<u32*>(g_key + bt.n_blue);
+        sort_block_kernel<<<h[3] < 148u * 2u ? h[3] : 148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, huge, counts + 3, g_key, g_tag, true);
+        CUDA_TRY(cudaFreeAsync(g_key, st));
         ++launched;
     }
     DEBWT_COUNT(launched);
