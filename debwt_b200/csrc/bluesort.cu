@@ -10,10 +10,13 @@
 // array from code 32 on.  Segments are binned by size:
 //   <= 32   : one warp, entries in registers, rank by counting;
 //   <= 128  : one warp, entries + cached words in shared memory, same-direction bitonic network;
-//   <= 4096 : one thread block, shared memory, round-based refinement: one cheap network per 32 codes on
-//             (tie group, code word) keys, so long common prefixes are walked once per entry, not per comparison;
-//   larger  : the same rounds over HBM; every aligned 4096-entry block of the segment is staged in shared
-//             memory once per merge level, only the stages with a longer partner distance run over HBM.
+//   larger  : round-based refinement (MSD style) driven by work lists: a work item is a run of entries that
+//             agree on their first `depth` codes; one block sorts it by the next 32 codes with a network whose
+//             comparisons touch no memory (<= 4096 entries entirely in shared memory; beyond that every
+//             aligned 4096-entry block is staged once per merge level and only the long-distance stages run
+//             over HBM); equal-word runs that still hold two prev symbols are finished by direct comparisons
+//             (<= 32 entries) or become the next round's items, so long common prefixes are walked once per
+//             entry instead of once per comparison and the work shrinks geometrically.
 // The network uses virtual +inf padding (all compare-exchanges point the same way), so no segment
 // needs scratch for padding.  Segments whose prev symbols are all equal are skipped
 // (src/sortBlue.c:192-219): any order gives the same BWT.
@@ -213,18 +216,6 @@ struct SegArrays {
     u32* tag;      // tie group id (position of the group's first entry) / plain flag for the fallback
 };
 
-struct LessGroupKey {
-    __device__ __forceinline__ bool operator()(u64, u64 ka, u32 ta, u64, u64 kb, u32 tb) const {
-        return ta != tb ? ta < tb : ka < kb;
-    }
-};
-struct LessCached {
-    SpView sp;
-    __device__ __forceinline__ bool operator()(u64 ea, u64 ka, u32 ta, u64 eb, u64 kb, u32 tb) const {
-        return entry_less(sp, ea, ka, ta != 0, eb, kb, tb != 0);
-    }
-};
-
 template <typename Less>
 __device__ __forceinline__ void cmpswap3(const SegArrays& a, u32 i, u32 l, const Less& less) {
     const u64 ei = a.ent[i], el = a.ent[l], ki = a.key[i], kl = a.key[l];
@@ -308,61 +299,90 @@ __device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool i
     }
 }
 
-__global__ void __launch_bounds__(BIG_TPB) sort_block_kernel(u64* __restrict__ blue, BranchTable bt, SpView sp,
-                                                            const u32* __restrict__ list, const u32* __restrict__ count,
-                                                            u64* __restrict__ g_key, u32* __restrict__ g_tag, bool in_hbm) {
+struct LessKey {
+    __device__ __forceinline__ bool operator()(u64, u64 ka, u32, u64, u64 kb, u32) const { return ka < kb; }
+};
+// comparator for items whose code words contain a separator: words at `depth` are cached in key (tag = plain)
+struct LessFromDepth {
+    SpView sp;
+    u32 depth;
+    __device__ __forceinline__ bool operator()(u64 ea, u64 ka, u32 ta, u64 eb, u64 kb, u32 tb) const {
+        if (ta && tb) {
+            if (ka != kb) return ka < kb;
+            return sp_less_from(sp, ea >> 4, eb >> 4, depth + 32);
+        }
+        return sp_less_from(sp, ea >> 4, eb >> 4, depth);
+    }
+};
+
+// A work item = a run of blue entries that agree on their first `depth` codes and still hold two different
+// prev symbols.  One block sorts it by the next 32 codes; the runs of equal words that come out are
+// finished (singletons, equal prev symbols), finished here by direct comparisons (<= 32 entries) or
+// appended to the next round's list.  Work shrinks geometrically from round to round.
+struct WorkItem {
+    u64 off;
+    u32 len, depth;
+};
+
+__global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u32* __restrict__ list, u32 n,
+                                                        WorkItem* __restrict__ items) {
+    const u32 i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const u32 b = list[i];
+    WorkItem w;
+    w.off = bt.blue[b];
+    w.len = bt.blue[b + 1] - bt.blue[b];
+    w.depth = 0;
+    items[i] = w;
+}
+
+__global__ void __launch_bounds__(BIG_TPB) refine_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
+                                                        u32 n_items, WorkItem* __restrict__ next, u32* __restrict__ next_count,
+                                                        u64* __restrict__ g_key, u32* __restrict__ g_tag) {
     extern __shared__ __align__(16) unsigned char blk_smem[];
     SegArrays s;
     s.ent = reinterpret_cast<u64*>(blk_smem);
     s.key = s.ent + CHUNK;
     s.tag = reinterpret_cast<u32*>(s.key + CHUNK);
-    __shared__ int s_flag[3];                      // [0] work left, [1] separator word seen, [2] scratch
-    const u32 n = *count;
-    for (u32 idx = blockIdx.x; idx < n; idx += gridDim.x) {
-        const u32 b = list[idx];
-        const u64 off = bt.blue[b];
-        const u32 len = (u32)(bt.blue[b + 1] - off);
+    __shared__ int s_flag, s_mixed;
+    for (u32 idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+        const WorkItem it = items[idx];
+        const u32 len = it.len, depth = it.depth;
+        const bool in_hbm = len > (u32)CHUNK;
         SegArrays g;
-        g.ent = blue + off;
-        g.key = in_hbm ? g_key + off : s.key;
-        g.tag = in_hbm ? g_tag + off : s.tag;
-        const SegArrays& w = in_hbm ? g : s;       // where the segment lives during the rounds
-        if (!in_hbm) {
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) s.ent[t] = g.ent[t];
-        }
-        for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = 0;      // one tie group
+        g.ent = blue + it.off;
+        g.key = in_hbm ? g_key + it.off : s.key;
+        g.tag = in_hbm ? g_tag + it.off : s.tag;
+        const SegArrays& w = in_hbm ? g : s;
+        if (threadIdx.x == 0) { s_flag = 0; s_mixed = 0; }
         __syncthreads();
-        bool fallback = false;
-        for (u32 depth = 0;; depth += 32) {
-            // fetch the code word at this depth for every entry that still sits in a tie group
-            if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[1] = 0; }
+        const u32 prev0 = (u32)(g.ent[0] & 15ull);
+        // ---- stage the entries and fetch their code word at this depth ----
+        for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+            const u64 e = g.ent[t];
+            if ((u32)(e & 15ull) != prev0) s_mixed = 1;
+            if (!in_hbm) s.ent[t] = e;
+            const u64 sidx = (e >> 4) + depth;
+            w.key[t] = text_window32(sp.codes, sidx);
+            const bool plain = fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes;
+            w.tag[t] = plain ? 1u : 0u;
+            if (!plain) s_flag = 1;
+        }
+        __syncthreads();
+        const bool fallback = s_flag != 0, mixed = s_mixed != 0;
+        __syncthreads();
+        if (!mixed) {
+            // every prev symbol equal: any order gives the same BWT (src/sortBlue.c:192-219)
+        } else if (fallback) {
+            LessFromDepth lf{sp, depth};
+            net_sort(g, s, len, !in_hbm, lf);           // final order for this item
+        } else {
+            net_sort(g, s, len, !in_hbm, LessKey());
+            // ---- runs of equal words: head index of every entry (max-scan over "own index if head") ----
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = (t == 0 || w.key[t] != w.key[t - 1]) ? 1u : 0u;
             __syncthreads();
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
-                const u32 gid = w.tag[t];
-                const bool tied = (t + 1 < len && w.tag[t + 1] == gid) || (t > 0 && w.tag[t - 1] == gid);
-                if (tied) {
-                    const u64 sidx = (w.ent[t] >> 4) + depth;
-                    w.key[t] = text_window32(sp.codes, sidx);
-                    if (fetch_sep(sp.sep, sidx)) s_flag[1] = 1;
-                    if (sidx >= sp.n_codes) s_flag[1] = 1;                      // unreachable; never walk off the code string
-                } else {
-                    w.key[t] = 0;
-                }
-            }
-            __syncthreads();
-            if (s_flag[1]) { fallback = true; break; }
-            net_sort(g, s, len, !in_hbm, LessGroupKey());
-            // renumber: tag = index of the run's first entry (keeps every group where it is).
-            // (1) mark run heads in the top bit of the tag (neighbours compare the low 31 bits only)
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
-                const bool head = t == 0 || ((w.tag[t] ^ w.tag[t - 1]) & 0x7fffffffu) || w.key[t] != w.key[t - 1];
-                if (head) w.tag[t] |= 0x80000000u;
-            }
-            __syncthreads();
-            // (2) inclusive max-scan of "own index if head else 0" (Hillis-Steele, ping-pong between the two
-            //     32-bit halves of the key words, which are free until the next fetch)
             u32* k32 = reinterpret_cast<u32*>(w.key);
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) k32[2 * t] = (w.tag[t] & 0x80000000u) ? t : 0u;
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) k32[2 * t] = w.tag[t] ? t : 0u;
             __syncthreads();
             u32 ph = 0;
             for (u32 d = 1; d < len; d <<= 1) {
@@ -375,55 +395,46 @@ __global__ void __launch_bounds__(BIG_TPB) sort_block_kernel(u64* __restrict__ b
                 ph ^= 1u;
             }
             for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = k32[2 * t + ph];
-            if (threadIdx.x == 0) { s_flag[0] = 0; s_flag[2] = 0; }
             __syncthreads();
-            // a tie group still needs work while it holds two different prev symbols; big ones go another
-            // round, small ones (<= 32 entries) are finished below with direct string comparisons
+            // ---- which runs still hold two different prev symbols (flag at the run head) ----
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) k32[2 * t] = 0u;
+            __syncthreads();
             for (u32 t = threadIdx.x + 1; t < len; t += blockDim.x) {
-                const u32 gid = w.tag[t];
-                if (gid == w.tag[t - 1] && ((w.ent[t] ^ w.ent[t - 1]) & 15ull)) {
-                    s_flag[0] = 1;
-                    if (gid + 32 < len && w.tag[gid + 32] == gid) s_flag[2] = 1;
-                }
+                const u32 h = w.tag[t];
+                if (h == w.tag[t - 1] && ((w.ent[t] ^ w.ent[t - 1]) & 15ull)) k32[2 * h] = 1u;
             }
             __syncthreads();
-            const int work_left = s_flag[0], big_left = s_flag[2];
-            __syncthreads();                       // everyone has read the flags before the next round resets them
-            if (!work_left) break;
-            if (!big_left) {
-                // every unresolved group fits a warp: rank by counting, comparing from the first unseen code on
-                const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-                for (u32 h = wid; h < len; h += nw) {
-                    if (w.tag[h] != h) continue;                                   // warp-uniform
-                    const bool mem = h + lane < len && w.tag[h + lane] == h;
-                    const u32 size = __popc(__ballot_sync(0xffffffffu, mem));
-                    if (size < 2) continue;
-                    const u64 e = mem ? w.ent[h + lane] : 0;
-                    const u32 c0 = __shfl_sync(0xffffffffu, (u32)(e & 15ull), 0);
-                    if (__all_sync(0xffffffffu, !mem || (u32)(e & 15ull) == c0)) continue;
-                    u32 rank = 0;
-                    for (u32 j = 0; j < size; ++j) {
-                        __syncwarp();
-                        const u64 ej = __shfl_sync(0xffffffffu, e, j);
-                        if (mem && j != lane && sp_less_from(sp, ej >> 4, e >> 4, depth + 32)) ++rank;
-                    }
-                    __syncwarp();
-                    if (mem) w.ent[h + rank] = e;
-                    __syncwarp();
-                }
-                __syncthreads();
-                break;
-            }
-        }
-        if (fallback) {
-            // comparator network from scratch: cached first word + plain flag, deep compares through '#'
+            // ---- long unresolved runs go to the next round (pushed by the run's last entry) ----
             for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
-                const Cached c = cache_of(sp, w.ent[t]);
-                w.key[t] = c.word; w.tag[t] = c.plain ? 1u : 0u;
+                const u32 h = w.tag[t];
+                if ((t + 1 == len || w.tag[t + 1] != h) && k32[2 * h]) {
+                    const u32 size = t + 1 - h;
+                    if (size > 32) {
+                        WorkItem nw;
+                        nw.off = it.off + h; nw.len = size; nw.depth = depth + 32;
+                        next[atomicAdd(next_count, 1u)] = nw;
+                    }
+                }
+            }
+            // ---- short unresolved runs: one warp each, rank by counting with direct string comparisons ----
+            const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwp = blockDim.x >> 5;
+            for (u32 h = wid; h < len; h += nwp) {
+                if (w.tag[h] != h || !k32[2 * h]) continue;                            // warp-uniform
+                const bool mem = h + lane < len && w.tag[h + lane] == h;
+                const u32 size = __popc(__ballot_sync(0xffffffffu, mem));
+                if (h + 32 < len && w.tag[h + 32] == h) continue;                      // long run: next round
+                const u64 e = mem ? w.ent[h + lane] : 0;
+                u32 rank = 0;
+                for (u32 j = 0; j < size; ++j) {
+                    __syncwarp();
+                    const u64 ej = __shfl_sync(0xffffffffu, e, j);
+                    if (mem && j != lane && sp_less_from(sp, ej >> 4, e >> 4, depth + 32)) ++rank;
+                }
+                __syncwarp();
+                if (mem) w.ent[h + rank] = e;
+                __syncwarp();
             }
             __syncthreads();
-            LessCached lc{sp};
-            net_sort(g, s, len, !in_hbm, lc);
         }
         if (!in_hbm) {
             for (u32 t = threadIdx.x; t < len; t += blockDim.x) g.ent[t] = s.ent[t];
@@ -453,20 +464,39 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
     if (h[1]) { sort_mid_kernel<<<blocks_for(h[1]), TPB, 0, st>>>(blue, bt, sp, mid, counts + 1); ++launched; }
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
+        CUDA_TRY(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
         attr_done = true;
     }
-    if (h[2]) {
-        sort_block_kernel<<<h[2] < 148u * 2u ? h[2] : 148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, block, counts + 2, nullptr, nullptr, false);
-        ++launched;
-    }
-    if (h[3]) {
+    const u32 n_big = h[2] + h[3];
+    if (n_big) {
+        // round-based refinement of the segments beyond one warp's shared-memory slice
+        const u64 cap = bt.n_blue / 32 + n_big + 16;
+        WorkItem* lists = nullptr;
+        u32* d_cnt = nullptr;
         u64* g_key = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_key), bt.n_blue * 12 + 64, st));
-        u32* g_tag = reinterpret_cast<u32*>(g_key + bt.n_blue);
-        sort_block_kernel<<<h[3] < 148u * 2u ? h[3] : 148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, bt, sp, huge, counts + 3, g_key, g_tag, true);
-        CUDA_TRY(cudaFreeAsync(g_key, st));
-        ++launched;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lists), 2 * cap * sizeof(WorkItem), st));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), 64, st));
+        if (h[3]) CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_key), bt.n_blue * 12 + 64, st));
+        u32* g_tag = g_key ? reinterpret_cast<u32*>(g_key + bt.n_blue) : nullptr;
+        WorkItem* cur = lists;
+        WorkItem* nxt = lists + cap;
+        if (h[2]) seed_items_kernel<<<(h[2] + TPB - 1) / TPB, TPB, 0, st>>>(bt, block, h[2], cur);
+        if (h[3]) seed_items_kernel<<<(h[3] + TPB - 1) / TPB, TPB, 0, st>>>(bt, huge, h[3], cur + h[2]);
+        launched += (h[2] ? 1 : 0) + (h[3] ? 1 : 0);
+        u32 n_items = n_big;
+        for (int round = 0; n_items && round < 100000; ++round) {
+            CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
+            refine_kernel<<<n_items < 148u * 2u ? n_items : 148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, sp, cur, n_items, nxt, d_cnt,
+                                                                                                    g_key, g_tag);
+            ++launched;
+            CUDA_TRY(cudaMemcpyAsync(&n_items, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (n_items > cap) { set_error("internal: K10 work list overflow"); return -1; }
+            WorkItem* t = cur; cur = nxt; nxt = t;
+        }
+        CUDA_TRY(cudaFreeAsync(lists, st));
+        CUDA_TRY(cudaFreeAsync(d_cnt, st));
+        if (g_key) CUDA_TRY(cudaFreeAsync(g_key, st));
     }
     DEBWT_COUNT(launched);
     CUDA_TRY(cudaGetLastError());
