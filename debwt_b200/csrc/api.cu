@@ -413,7 +413,7 @@ int debwt_build(debwt_ctx* c, int k) {
     }
     if (dalloc(pool, &bt.kmer, bt.n_branch + 1) || dalloc(pool, &bt.head, bt.n_branch + 1) ||
         dalloc(pool, &bt.blue, bt.n_branch + 2) || dalloc(pool, &bt.cursor, bt.n_branch + 1) ||
-        dalloc(pool, &bt.bidx, (1ull << bt.bits) + 2))
+        dalloc(pool, &bt.bidx, BranchTable::index_words(bt.bits)))
         return -1;
     CUDA_TRY(cudaMemsetAsync(bt.cursor, 0, (bt.n_branch + 1) * 4, st));
     if (k_branch_write(d_keys, nk, d_gmask, d_brws, bt, st)) return -1;

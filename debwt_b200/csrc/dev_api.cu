@@ -158,6 +158,8 @@ int debwt_dev_branch_write(const void* d_sorted, uint64_t n, const void* d_gmask
     return 0;
 }
 
+uint64_t debwt_dev_branch_index_words(int bits) { return BranchTable::index_words(bits); }
+
 int debwt_dev_branch_index(const void* d_kmer, uint64_t n_branch, void* d_bidx_u32, int bits, void* stream) {
     return k_branch_index(BT(d_kmer, nullptr, nullptr, nullptr, d_bidx_u32, bits, n_branch, 0), S(stream));
 }

@@ -480,6 +480,13 @@ __global__ void __launch_bounds__(TPB) branch_index_kernel(BranchTable bt) {
     bt.bidx[t] = (t == nb) ? (u32)bt.n_branch : (u32)lower_bound_u64(bt.kmer, 0, bt.n_branch, t << (64 - bt.bits));
 }
 
+__global__ void __launch_bounds__(TPB) branch_filter_kernel(BranchTable bt) {
+    const u64 b = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (b >= bt.n_branch) return;
+    const u64 f = bt.kmer[b] >> (64 - BranchTable::filter_bits(bt.bits));
+    atomicOr(bt.filter() + (f >> 5), 1u << (f & 31));
+}
+
 __global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki,
                                                          const u64* __restrict__ pads, u64 m, u64* __restrict__ ins) {
     const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
@@ -563,7 +570,9 @@ int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, 
 
 int k_branch_index(BranchTable bt, cudaStream_t st) {
     branch_index_kernel<<<grid_for((1ull << bt.bits) + 1, TPB), TPB, 0, st>>>(bt);
-    DEBWT_COUNT(1);
+    CUDA_TRY(cudaMemsetAsync(bt.filter(), 0, (1ull << (BranchTable::filter_bits(bt.bits) - 5)) * 4, st));
+    if (bt.n_branch) branch_filter_kernel<<<grid_for(bt.n_branch, TPB), TPB, 0, st>>>(bt);
+    DEBWT_COUNT(2);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

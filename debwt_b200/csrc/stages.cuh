@@ -54,8 +54,12 @@ struct BranchTable {
     u32* head = nullptr;   // [B]  index of the group's first sorted key
     u32* blue = nullptr;   // [B+1] exclusive prefix of blue-segment sizes (0 for non multi-in)
     u32* cursor = nullptr; // [B]  fill cursor per segment
-    u32* bidx = nullptr;   // [2^bits + 1] direct index on the top `bits` bits of the k-mer
+    u32* bidx = nullptr;   // [2^bits + 2] direct index on the top `bits` bits of the k-mer, followed by the
+                           // presence bitmap: one bit per value of the top filter_bits(bits) bits
     int bits = 0;
+    __host__ __device__ static int filter_bits(int bits) { return bits + 3 < 30 ? bits + 3 : 30; }
+    __host__ __device__ static u64 index_words(int bits) { return (1ull << bits) + 2 + (1ull << (filter_bits(bits) - 5)); }
+    __host__ __device__ u32* filter() const { return bidx + (1ull << bits) + 2; }
 };
 size_t branch_workspace_bytes(u64 n);
 // pass 1: counts (B, M) -> d_totals[0], d_totals[1]

@@ -284,7 +284,7 @@ class CudaOps:
         bits = 8
         while bits < 27 and (1 << bits) < 2 * B:
             bits += 1
-        bidx = self.empty((1 << bits) + 2, torch.int32)
+        bidx = self.empty(self._bytes("debwt_dev_branch_index_words", bits), torch.int32)
         self._ck(self.L.debwt_dev_branch_index(_p(gkmer), _u64(B), _p(bidx), bits, self._st()))
         return bidx, bits
 

@@ -59,6 +59,8 @@ int debwt_dev_branch_count(const void* d_sorted, uint64_t n, const void* d_gmask
                            void* d_workspace, void* stream);
 int debwt_dev_branch_write(const void* d_sorted, uint64_t n, const void* d_gmask, void* workspace, void* d_kmer,
                            void* d_head_u32, void* d_blue_u32 /* B+1 */, uint64_t n_branch, uint64_t n_blue, void* stream);
+/* d_bidx_u32 holds debwt_dev_branch_index_words(bits) words: the direct index followed by a presence bitmap */
+uint64_t debwt_dev_branch_index_words(int bits);
 int debwt_dev_branch_index(const void* d_kmer, uint64_t n_branch, void* d_bidx_u32, int bits, void* stream);
 /* sentinel-window suffixes: 32 R records of 32 bytes {w0,w1,ins,rank,prev,next} (ins is local to d_sorted) */
 int debwt_dev_special_scan(const void* d_words, const void* d_seps, uint64_t n_rec, const void* d_sorted, uint64_t n,
