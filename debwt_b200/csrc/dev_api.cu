@@ -90,24 +90,39 @@ int debwt_dev_owner_of_index(void* d_idx, uint64_t n, const void* d_bases, uint3
     return k_owner_of_index(P64(d_idx), n, P64(d_bases), n_ranks, P8(d_dest_u8), S(stream));
 }
 
-int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8, uint64_t n, uint32_t n_ranks,
-                        void* d_out_a, void* d_out_b, uint64_t* counts_out, void* d_workspace, void* stream) {
-    if (n_ranks == 0 || n_ranks > 16) { set_error("debwt_dev_partition: 1..16 ranks"); return -1; }
-    cudaStream_t st = S(stream);
+namespace {
+int partition_impl(const u64* a, const u64* b, const PartitionBy& by, u64 n, u32 n_ranks, u64* out_a, u64* out_b,
+                   uint64_t* counts_out, void* d_workspace, cudaStream_t st) {
+    if (n_ranks == 0 || n_ranks > 16) { set_error("partition: 1..16 ranks"); return -1; }
     u64* d_counts = P64(d_workspace);
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, 16 * 8, st));
-    if (k_partition_count(P8(d_dest_u8), n, d_counts, st)) return -1;
+    if (k_partition_count(a, by, n, n_ranks, d_counts, st)) return -1;
     u64 h[16];
     CUDA_TRY(cudaMemcpyAsync(h, d_counts, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     u64 cur[16], run = 0;
     for (int r = 0; r < 16; ++r) { cur[r] = run; run += h[r]; if ((u32)r < n_ranks) counts_out[r] = h[r]; }
     CUDA_TRY(cudaMemcpyAsync(d_counts, cur, sizeof cur, cudaMemcpyHostToDevice, st));
-    if (k_partition_scatter(P64(d_a), d_b ? P64(d_b) : nullptr, P8(d_dest_u8), n, d_counts, P64(d_out_a),
-                            d_out_b ? P64(d_out_b) : nullptr, st))
-        return -1;
+    if (k_partition_scatter(a, b, by, n, n_ranks, d_counts, out_a, out_b, st)) return -1;
     CUDA_TRY(cudaStreamSynchronize(st));     // `cur` lives on this stack frame
     return 0;
+}
+}  // namespace
+
+int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8, uint64_t n, uint32_t n_ranks,
+                        void* d_out_a, void* d_out_b, uint64_t* counts_out, void* d_workspace, void* stream) {
+    PartitionBy by;
+    by.dest = P8(d_dest_u8);
+    return partition_impl(P64(d_a), d_b ? P64(d_b) : nullptr, by, n, n_ranks, P64(d_out_a), d_out_b ? P64(d_out_b) : nullptr,
+                          counts_out, d_workspace, S(stream));
+}
+
+int debwt_dev_partition_by_splitters(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
+                                     int drop_marker, uint32_t n_ranks, void* d_out, uint64_t* counts_out, void* d_workspace,
+                                     void* stream) {
+    PartitionBy by;
+    by.splitters = P64(d_splitters); by.n_split = n_split; by.mask = mask; by.drop_marker = drop_marker != 0;
+    return partition_impl(P64(d_items), nullptr, by, n, n_ranks, P64(d_out), nullptr, counts_out, d_workspace, S(stream));
 }
 
 int debwt_dev_key_index_bits(uint64_t n) { return key_index_bits(n); }

@@ -55,49 +55,96 @@ constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = TPB * PART_ITEMS;
 constexpr int MAX_RANKS = 16;
 
-__global__ void __launch_bounds__(TPB) partition_count_kernel(const u8* __restrict__ dest, u64 n, u64* __restrict__ counts) {
+// Owner of an item: from a precomputed byte array, or on the fly from the splitters.
+struct OwnerFn {
+    const u8* dest;            // non-null: precomputed owners
+    const u64* splitters;      // else: owner = number of splitters <= (item & mask)
+    u32 n_split;
+    u64 mask;
+    bool drop_marker;          // items equal to ~0 are dropped
+    __device__ __forceinline__ u32 operator()(const u64* __restrict__ items, u64 i) const {
+        if (dest) return dest[i];
+        const u64 v = items[i];
+        if (drop_marker && v == ~0ull) return 255u;
+        u32 lo = 0;
+        for (u32 sidx = 0; sidx < n_split; ++sidx) lo += (splitters[sidx] <= (v & mask)) ? 1u : 0u;   // <= 15 splitters
+        return lo;
+    }
+};
+
+// Warp-aggregated counting: one ballot per destination, lane g keeps the count of destination g.
+__global__ void __launch_bounds__(TPB) partition_count_kernel(const u64* __restrict__ items, OwnerFn owner, u64 n, u32 n_ranks,
+                                                             u64* __restrict__ counts) {
     __shared__ u32 s[MAX_RANKS];
     if (threadIdx.x < MAX_RANKS) s[threadIdx.x] = 0;
     __syncthreads();
+    const u32 lane = threadIdx.x & 31;
     const u64 base = (u64)blockIdx.x * PART_TILE;
+    u32 mine = 0;
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         const u64 i = base + (u64)j * TPB + threadIdx.x;
-        if (i < n) { const u32 d = dest[i]; if (d < MAX_RANKS) atomicAdd(&s[d], 1u); }
+        const u32 d = i < n ? owner(items, i) : 255u;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 b = __ballot_sync(0xffffffffu, d == g);
+            if (lane == g) mine += __popc(b);
+        }
     }
+    if (lane < n_ranks && mine) atomicAdd(&s[lane], mine);
     __syncthreads();
-    if (threadIdx.x < MAX_RANKS && s[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)s[threadIdx.x]);
+    if (threadIdx.x < n_ranks && s[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)s[threadIdx.x]);
 }
 
-// cursors[d] starts at the exclusive prefix of counts; every block reserves one chunk per owner
+// cursors[d] starts at the exclusive prefix of counts; every block reserves one chunk per owner and keeps
+// the items of one (block, owner) pair in their original order
 __global__ void __launch_bounds__(TPB) partition_scatter_kernel(const u64* __restrict__ a, const u64* __restrict__ b,
-                                                               const u8* __restrict__ dest, u64 n,
+                                                               OwnerFn owner, u64 n, u32 n_ranks,
                                                                u64* __restrict__ cursors, u64* __restrict__ out_a,
                                                                u64* __restrict__ out_b) {
-    __shared__ u32 s_cnt[MAX_RANKS];
+    constexpr int NW = TPB / 32;
+    __shared__ u32 s_wcnt[NW][MAX_RANKS];
     __shared__ u64 s_base[MAX_RANKS];
-    if (threadIdx.x < MAX_RANKS) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
     const u64 base = (u64)blockIdx.x * PART_TILE;
-    u32 slot[PART_ITEMS];
     u8 dd[PART_ITEMS];
+    u32 mine = 0;
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         const u64 i = base + (u64)j * TPB + threadIdx.x;
-        dd[j] = 255;
-        if (i < n) { dd[j] = dest[i]; if (dd[j] < MAX_RANKS) slot[j] = atomicAdd(&s_cnt[dd[j]], 1u); }
+        const u32 d = i < n ? owner(a, i) : 255u;
+        dd[j] = (u8)d;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 bal = __ballot_sync(0xffffffffu, d == g);
+            if (lane == g) mine += __popc(bal);
+        }
+    }
+    if (lane < MAX_RANKS) s_wcnt[warp][lane] = lane < n_ranks ? mine : 0;
+    __syncthreads();
+    if (threadIdx.x < n_ranks) {
+        u32 run = 0;
+        for (int w = 0; w < NW; ++w) { const u32 c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
+        s_base[threadIdx.x] = run ? atomicAdd(&cursors[threadIdx.x], (u64)run) : 0;
     }
     __syncthreads();
-    if (threadIdx.x < MAX_RANKS) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (u64)s_cnt[threadIdx.x]) : 0;
-    __syncthreads();
+    u32 run = lane < n_ranks ? s_wcnt[warp][lane] : 0;      // lane g: next free slot of destination g inside this block
 #pragma unroll
     for (int j = 0; j < PART_ITEMS; ++j) {
         const u64 i = base + (u64)j * TPB + threadIdx.x;
-        if (i < n && dd[j] < MAX_RANKS) {
-            const u64 o = s_base[dd[j]] + slot[j];
+        const u32 d = dd[j];
+        u32 rank = 0, add = 0;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 bal = __ballot_sync(0xffffffffu, d == g);
+            if (d == g) rank = __popc(bal & lt);
+            if (lane == g) add = __popc(bal);
+        }
+        const u32 start = __shfl_sync(0xffffffffu, run, d < n_ranks ? d : 0);
+        if (d < n_ranks) {
+            const u64 o = s_base[d] + start + rank;
             out_a[o] = a[i];
             if (b) out_b[o] = b[i];
         }
+        run += add;
     }
 }
 
@@ -320,16 +367,25 @@ int k_owner_of_index(u64* idx, u64 n, const u64* d_bases, u32 n_ranks, u8* dest,
     LAUNCHED(1);
 }
 
-int k_partition_count(const u8* dest, u64 n, u64* d_counts /* MAX_RANKS, zeroed */, cudaStream_t st) {
+namespace {
+OwnerFn make_owner(const PartitionBy& by) {
+    OwnerFn f;
+    f.dest = by.dest; f.splitters = by.splitters; f.n_split = by.n_split; f.mask = by.mask; f.drop_marker = by.drop_marker;
+    return f;
+}
+}  // namespace
+
+int k_partition_count(const u64* items, const PartitionBy& by, u64 n, u32 n_ranks, u64* d_counts /* MAX_RANKS, zeroed */,
+                      cudaStream_t st) {
     if (n == 0) return 0;
-    partition_count_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(dest, n, d_counts);
+    partition_count_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(items, make_owner(by), n, n_ranks, d_counts);
     LAUNCHED(1);
 }
 
-int k_partition_scatter(const u64* a, const u64* b, const u8* dest, u64 n, u64* d_cursors, u64* out_a, u64* out_b,
-                        cudaStream_t st) {
+int k_partition_scatter(const u64* a, const u64* b, const PartitionBy& by, u64 n, u32 n_ranks, u64* d_cursors, u64* out_a,
+                        u64* out_b, cudaStream_t st) {
     if (n == 0) return 0;
-    partition_scatter_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, b, dest, n, d_cursors, out_a, out_b);
+    partition_scatter_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, b, make_owner(by), n, n_ranks, d_cursors, out_a, out_b);
     LAUNCHED(1);
 }
 

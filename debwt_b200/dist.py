@@ -242,6 +242,15 @@ class CudaOps:
                                             _p(out_b) if out_b is not None else ctypes.c_void_p(0), counts, _p(ws), self._st()))
         return out_a, out_b, [int(counts[i]) for i in range(n_ranks)]
 
+    def partition_by_splitters(self, items, splitters, n_split, mask, drop_marker, n_ranks):
+        out = torch.empty_like(items)
+        counts = (ctypes.c_uint64 * 16)()
+        ws = self.empty(32)
+        self._ck(self.L.debwt_dev_partition_by_splitters(_p(items), _u64(items.numel()), _p(splitters), ctypes.c_uint32(n_split),
+                                                         _u64(mask), int(bool(drop_marker)), ctypes.c_uint32(n_ranks), _p(out),
+                                                         counts, _p(ws), self._st()))
+        return out, [int(counts[i]) for i in range(n_ranks)]
+
     def key_index(self, sorted_keys):
         n = sorted_keys.numel()
         bits = int(self.L.debwt_dev_key_index_bits(_u64(n)))
@@ -485,20 +494,15 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     d_split = ops.from_numpy(splitters_np) if G > 1 else ops.zeros(1)
     n_split = G - 1
 
-    def owner(items, mask, drop_marker):
-        if G == 1:
-            d = ops.zeros(items.numel(), torch.uint8)
-            if drop_marker and items.numel():
-                d[items == I64_ALL_ONES] = 255
-            return d
-        return ops.owner_of_keys(items, d_split[:n_split], mask, drop_marker)
+    def route(items, drop_marker):
+        """items grouped by the owner of their k-mer (top 62 bits) + the per-owner counts"""
+        return ops.partition_by_splitters(items, d_split, n_split, 0xFFFFFFFFFFFFFFFC, drop_marker, G)
 
     tick('extract+splitters')
     # 3. one all-to-all: every key goes to the owner of its k-mer
-    dest = owner(keys, 0xFFFFFFFFFFFFFFFC, False)
-    part, _, counts = ops.partition(keys, None, dest, G)
+    part, counts = route(keys, False)
     mine, _ = comm.all_to_all_v(part, counts)
-    del keys, part, dest
+    del keys, part
     tick('partition+alltoall')
     n_loc = int(mine.numel())
     sk = ops.sort(mine, True) if getattr(ops, "timed_main_sort", False) else ops.sort(mine)
@@ -514,8 +518,7 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     tick('c.index')
     q = ops.out_edges_queries(sk, gmask) if n_loc else ops.empty(0)
     tick('c.out_edges')
-    dq = owner(q, 0xFFFFFFFFFFFFFFFC, True)
-    qpart, _, qcounts = ops.partition(q, None, dq, G)
+    qpart, qcounts = route(q, True)
     tick('c.partition')
     qrecv, _ = comm.all_to_all_v(qpart, qcounts)
     tick('c.alltoall')
@@ -524,7 +527,7 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
         tick('c.apply')
         ops.heads_tails(words, d_seps, R, sk, ki, gmask)
         ops.propagate(sk, gmask)
-    del q, qpart, qrecv, dq
+    del q, qpart, qrecv
     tick('c.propagate')
     bt = ops.branch_table(sk, gmask)
     tick('c.branch')

@@ -44,6 +44,10 @@ int debwt_dev_owner_of_index(void* d_idx, uint64_t n, const void* d_bases, uint3
    d_workspace: 128 bytes */
 int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8, uint64_t n, uint32_t n_ranks,
                         void* d_out_a, void* d_out_b, uint64_t* counts_out, void* d_workspace, void* stream);
+/* same for 64-bit items whose owner is the number of splitters <= (item & mask), computed on the fly */
+int debwt_dev_partition_by_splitters(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
+                                     int drop_marker, uint32_t n_ranks, void* d_out, uint64_t* counts_out, void* d_workspace,
+                                     void* stream);
 /* direct index over sorted keys */
 int debwt_dev_key_index_bits(uint64_t n);
 int debwt_dev_key_index(const void* d_sorted, uint64_t n, void* d_idx_u32, int bits, void* stream);

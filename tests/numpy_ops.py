@@ -114,6 +114,11 @@ class NumpyOps:
         g[:] = g - b[r]
         return torch.from_numpy(r.astype(np.uint8))
 
+    def partition_by_splitters(self, items, splitters, n_split, mask, drop_marker, n_ranks):
+        dest = self.owner_of_keys(items, splitters[:n_split], mask, drop_marker)
+        out, _, counts = self.partition(items, None, dest, n_ranks)
+        return out, counts
+
     def partition(self, a, b, dest, n_ranks):
         d = dest.numpy()
         keep = d < n_ranks
