@@ -278,7 +278,7 @@ def ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": world * n_bases / (ms_dev * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": desc, "n_bases": n_bases, "n_records": len(records), "k": 32,
                        "l2": "inputs larger than L2 (text %d MB, keys %d MB per step)" % (n // 2**20, 8 * nk // 2**20),
                        "parallelism": "replicas" if world > 1 else "single GPU",

@@ -382,8 +382,8 @@ int debwt_build(debwt_ctx* c, int k) {
     S.sort_sweeps = (u32)sweeps;
     pool.release(d_sortws);
     pool.release(d_keys == d_ka ? d_kb : d_ka);
-    u32 h_err = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    u32 h_err[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h_err, d_err, 8, cudaMemcpyDeviceToHost, st));
     mark();                                                                     // ev3
 
     // ---- K5/K6 edge marks, K7 branch table ----
@@ -402,7 +402,8 @@ int debwt_build(debwt_ctx* c, int k) {
     u64 h_tot[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (h_err) FAIL("input contains a symbol other than A, C, G, T (either case)");
+    if (h_err[0]) FAIL("input contains a symbol other than A, C, G, T (either case)");
+    if (h_err[1] != R) FAIL("input contains '#' or '$' inside a record (they are reserved for the record separators)");
     BranchTable bt;
     bt.n_branch = h_tot[0]; bt.n_blue = h_tot[1];
     S.n_branch = bt.n_branch; S.n_blue = bt.n_blue;

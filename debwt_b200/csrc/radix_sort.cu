@@ -359,6 +359,11 @@ int sort_config_tile(int cfg) {
         case 6: return 512 * 16;
         case 8: return 384 * 16;
         case 9: return 512 * 20;
+        case 10: case 11: return 320 * 16;
+        case 12: return 384 * 14;
+        case 13: return 448 * 12;
+        case 14: return 288 * 16;
+        case 15: return 384 * 18;
         default: return 256 * 16;
     }
 }
@@ -420,6 +425,12 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
             case 7: rc = launch_sweep<256, 16, 4>(src, dst, n, p, ws, st); break;
             case 8: rc = launch_sweep<384, 16, 3>(src, dst, n, p, ws, st); break;
             case 9: rc = launch_sweep<512, 20, 2>(src, dst, n, p, ws, st); break;
+            case 10: rc = launch_sweep<320, 16, 3>(src, dst, n, p, ws, st); break;
+            case 11: rc = launch_sweep<320, 16, 4>(src, dst, n, p, ws, st); break;
+            case 12: rc = launch_sweep<384, 14, 3>(src, dst, n, p, ws, st); break;
+            case 13: rc = launch_sweep<448, 12, 3>(src, dst, n, p, ws, st); break;
+            case 14: rc = launch_sweep<288, 16, 4>(src, dst, n, p, ws, st); break;
+            case 15: rc = launch_sweep<384, 18, 3>(src, dst, n, p, ws, st); break;
             default: rc = launch_sweep<256, 16, 3>(src, dst, n, p, ws, st); break;
         }
         if (rc) return rc;

@@ -103,7 +103,7 @@ int scan_exclusive_u32(const u32* in, u32* out, u64 m, bool popc, void* workspac
 // =============================================================================================
 namespace {
 
-__device__ __forceinline__ u32 base_code(u32 c, u32& bad) {
+__device__ __forceinline__ u32 base_code(u32 c, u32& bad, u32& nsep) {
     // A/a C/c G/g T/t -> 0 1 2 3; '#' '$' (separators) are stored as T like the reference does
     u32 u = c & 0xDFu;
     u32 code = (u >> 1) & 3u;
@@ -111,6 +111,7 @@ __device__ __forceinline__ u32 base_code(u32 c, u32& bad) {
     bool ok = (u == 0x41u) | (u == 0x43u) | (u == 0x47u) | (u == 0x54u);
     bool sep = (c == 0x23u) | (c == 0x24u);
     bad |= (u32)(!ok && !sep);
+    nsep += (u32)sep;
     return ok ? code : 3u;
 }
 
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii,
     if (w >= nwords) return;
     const u64 base = w * 32;
     u64 out = 0;
-    u32 bad = 0;
+    u32 bad = 0, nsep = 0;
     if (base + 32 <= n) {
         const uint4* p = reinterpret_cast<const uint4*>(ascii + base);
         uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -130,19 +131,20 @@ __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii,
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 u32 c = (v[q] >> (8 * r)) & 255u;
-                out = (out << 2) | base_code(c, bad);
+                out = (out << 2) | base_code(c, bad, nsep);
             }
         }
     } else {
         for (int j = 0; j < 32; ++j) {
             u64 i = base + j;
             u32 code = (i < n + 32) ? 3u : 0u;      // exactly 32 T of padding past the end (src/collect#$.c:87-90)
-            if (i < n) code = base_code(ascii[i], bad);
+            if (i < n) code = base_code(ascii[i], bad, nsep);
             out = (out << 2) | code;
         }
     }
     words[w] = out;
     if (bad) atomicOr(err, 1u);
+    if (nsep) atomicAdd(err + 1, nsep);        // separator bytes seen: must equal the number of records
 }
 
 // =============================================================================================

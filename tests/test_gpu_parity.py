@@ -219,6 +219,8 @@ def test_bwt_errors():
     with pytest.raises(DebwtError):
         api.build_bwt(["ACGTN" * 20])
     with pytest.raises(DebwtError):
+        api.build_bwt(["ACGT" * 10 + "#" + "ACGT" * 10])      # separators are reserved
+    with pytest.raises(DebwtError):
         api.build_bwt([])
     with pytest.raises(DebwtError):
         with api.BwtBuilder() as b:
