@@ -1,4 +1,6 @@
 // include/debwt_b200_dev.h: device-pointer stage ABI for the sharded path (thin wrappers).
+#include <string.h>
+
 #include <vector>
 
 #include "../../include/debwt_b200_dev.h"
@@ -123,6 +125,61 @@ int debwt_dev_partition_by_splitters(const void* d_items, uint64_t n, const void
     PartitionBy by;
     by.splitters = P64(d_splitters); by.n_split = n_split; by.mask = mask; by.drop_marker = drop_marker != 0;
     return partition_impl(P64(d_items), nullptr, by, n, n_ranks, P64(d_out), nullptr, counts_out, d_workspace, S(stream));
+}
+
+int debwt_dev_ipc_alloc(uint64_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size is part of the ABI");
+    CUDA_TRY(cudaMalloc(d_ptr, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+int debwt_dev_ipc_open(const unsigned char handle[64], void** d_ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int debwt_dev_ipc_close(void* d_ptr) {
+    CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int debwt_dev_ipc_free(void* d_ptr) {
+    CUDA_TRY(cudaFree(d_ptr));
+    return 0;
+}
+
+int debwt_dev_partition_count(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
+                              int drop_marker, uint32_t n_ranks, uint64_t* counts_out, void* d_workspace, void* stream) {
+    if (n_ranks == 0 || n_ranks > 16) { set_error("partition: 1..16 ranks"); return -1; }
+    cudaStream_t st = S(stream);
+    PartitionBy by;
+    by.splitters = P64(d_splitters); by.n_split = n_split; by.mask = mask; by.drop_marker = drop_marker != 0;
+    u64* d_counts = P64(d_workspace);
+    CUDA_TRY(cudaMemsetAsync(d_counts, 0, 16 * 8, st));
+    if (k_partition_count(P64(d_items), by, n, n_ranks, d_counts, st)) return -1;
+    u64 h[16];
+    CUDA_TRY(cudaMemcpyAsync(h, d_counts, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (u32 r = 0; r < n_ranks; ++r) counts_out[r] = h[r];
+    return 0;
+}
+
+int debwt_dev_partition_scatter_p2p(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
+                                    int drop_marker, uint32_t n_ranks, void* const* dst, void* d_workspace, void* stream) {
+    if (n_ranks == 0 || n_ranks > 16) { set_error("partition: 1..16 ranks"); return -1; }
+    cudaStream_t st = S(stream);
+    PartitionBy by;
+    by.splitters = P64(d_splitters); by.n_split = n_split; by.mask = mask; by.drop_marker = drop_marker != 0;
+    u64* d_cursors = P64(d_workspace);
+    CUDA_TRY(cudaMemsetAsync(d_cursors, 0, 16 * 8, st));
+    u64* d[16];
+    for (u32 r = 0; r < n_ranks; ++r) d[r] = P64(dst[r]);
+    return k_partition_scatter_p2p(P64(d_items), by, n, n_ranks, d_cursors, d, st);
 }
 
 int debwt_dev_key_index_bits(uint64_t n) { return key_index_bits(n); }

@@ -148,6 +148,59 @@ __global__ void __launch_bounds__(TPB) partition_scatter_kernel(const u64* __res
     }
 }
 
+// Fused bucket + exchange: same ordering logic as partition_scatter_kernel, but every destination has its
+// own base pointer -- the receive buffer of that rank, mapped into this process through CUDA IPC -- so
+// the keys cross NVLink as coalesced peer stores straight from the partition kernel; no staging buffer,
+// no separate all-to-all.  dst[d] already points at this rank's slot inside rank d's buffer.
+struct PeerDst {
+    u64* ptr[MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(TPB) partition_scatter_p2p_kernel(const u64* __restrict__ a, OwnerFn owner, u64 n, u32 n_ranks,
+                                                                   u64* __restrict__ cursors, PeerDst dst) {
+    constexpr int NW = TPB / 32;
+    __shared__ u32 s_wcnt[NW][MAX_RANKS];
+    __shared__ u64 s_base[MAX_RANKS];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+    const u64 base = (u64)blockIdx.x * PART_TILE;
+    u8 dd[PART_ITEMS];
+    u32 mine = 0;
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        const u64 i = base + (u64)j * TPB + threadIdx.x;
+        const u32 d = i < n ? owner(a, i) : 255u;
+        dd[j] = (u8)d;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 bal = __ballot_sync(0xffffffffu, d == g);
+            if (lane == g) mine += __popc(bal);
+        }
+    }
+    if (lane < MAX_RANKS) s_wcnt[warp][lane] = lane < n_ranks ? mine : 0;
+    __syncthreads();
+    if (threadIdx.x < n_ranks) {
+        u32 run = 0;
+        for (int w = 0; w < NW; ++w) { const u32 c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
+        s_base[threadIdx.x] = run ? atomicAdd(&cursors[threadIdx.x], (u64)run) : 0;
+    }
+    __syncthreads();
+    u32 run = lane < n_ranks ? s_wcnt[warp][lane] : 0;
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        const u64 i = base + (u64)j * TPB + threadIdx.x;
+        const u32 d = dd[j];
+        u32 rank = 0, add = 0;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 bal = __ballot_sync(0xffffffffu, d == g);
+            if (d == g) rank = __popc(bal & lt);
+            if (lane == g) add = __popc(bal);
+        }
+        const u32 start = __shfl_sync(0xffffffffu, run, d < n_ranks ? d : 0);
+        if (d < n_ranks) dst.ptr[d][s_base[d] + start + rank] = a[i];
+        run += add;
+    }
+}
+
 // ---- K5/K6 split into a local half and an exchanged half --------------------------------------
 __global__ void __launch_bounds__(TPB) out_edges_queries_kernel(const u64* __restrict__ k, u64 n, u16* __restrict__ gmask,
                                                                u64* __restrict__ queries) {
@@ -179,7 +232,8 @@ __global__ void __launch_bounds__(TPB) flag_slice_kernel(const u64* __restrict__
                                                         u32* __restrict__ mo_bits, u64* __restrict__ rec_entry,
                                                         u64* __restrict__ rec_index, u64* __restrict__ rec_count) {
     const u64 p = pos_lo + (u64)blockIdx.x * TPB + threadIdx.x;     // pos_lo is a multiple of 32
-    bool mo = false;
+    bool mo = false, mi = false;
+    u64 entry = 0, index = 0;
     if (p < pos_hi) {
         const u64 r = record_of(seps, n_rec, p);
         if (r < n_rec && p + KMER <= seps[r]) {
@@ -193,15 +247,28 @@ __global__ void __launch_bounds__(TPB) flag_slice_kernel(const u64* __restrict__
                     u32 prev;
                     if (p == start) prev = r ? 4u : 5u;
                     else prev = text_symbol(words, p - 1);
-                    const u64 slot = atomicAdd(rec_count, 1ull);
-                    rec_entry[slot] = (p << 4) | prev;
-                    rec_index[slot] = b;                             // index into the global branch table
+                    mi = true;
+                    entry = (p << 4) | prev;
+                    index = b;                                       // index into the global branch table
                 }
             }
         }
     }
+    // warp-aggregated append: one atomic per warp instead of one per record
+    const u32 lane = threadIdx.x & 31;
+    const u32 bmi = __ballot_sync(0xffffffffu, mi);
+    if (bmi) {
+        u64 base = 0;
+        if (lane == (u32)(__ffs(bmi) - 1)) base = atomicAdd(rec_count, (u64)__popc(bmi));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bmi) - 1);
+        if (mi) {
+            const u64 slot = base + __popc(bmi & lanemask_lt());
+            rec_entry[slot] = entry;
+            rec_index[slot] = index;
+        }
+    }
     const u32 bal = __ballot_sync(0xffffffffu, mo);
-    if ((threadIdx.x & 31) == 0) mo_bits[(p - pos_lo) >> 5] = bal;
+    if (lane == 0) mo_bits[(p - pos_lo) >> 5] = bal;
 }
 
 __global__ void __launch_bounds__(TPB) patch_bits_slice_kernel(u32* __restrict__ mo_bits, u64 pos_lo, u64 pos_hi,
@@ -386,6 +453,15 @@ int k_partition_scatter(const u64* a, const u64* b, const PartitionBy& by, u64 n
                         u64* out_b, cudaStream_t st) {
     if (n == 0) return 0;
     partition_scatter_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, b, make_owner(by), n, n_ranks, d_cursors, out_a, out_b);
+    LAUNCHED(1);
+}
+
+int k_partition_scatter_p2p(const u64* a, const PartitionBy& by, u64 n, u32 n_ranks, u64* d_cursors /* zeroed */,
+                            u64* const* dst, cudaStream_t st) {
+    if (n == 0) return 0;
+    PeerDst pd;
+    for (u32 r = 0; r < MAX_RANKS; ++r) pd.ptr[r] = r < n_ranks ? dst[r] : nullptr;
+    partition_scatter_p2p_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd);
     LAUNCHED(1);
 }
 

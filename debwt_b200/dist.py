@@ -251,6 +251,19 @@ class CudaOps:
                                                          counts, _p(ws), self._st()))
         return out, [int(counts[i]) for i in range(n_ranks)]
 
+    def partition_count(self, items, splitters, n_split, mask, drop_marker, n_ranks):
+        counts = (ctypes.c_uint64 * 16)()
+        ws = self.empty(32)
+        self._ck(self.L.debwt_dev_partition_count(_p(items), _u64(items.numel()), _p(splitters), ctypes.c_uint32(n_split), _u64(mask),
+                                                  int(bool(drop_marker)), ctypes.c_uint32(n_ranks), counts, _p(ws), self._st()))
+        return [int(counts[i]) for i in range(n_ranks)]
+
+    def partition_scatter_p2p(self, items, splitters, n_split, mask, drop_marker, n_ranks, dst):
+        ws = self.empty(32)
+        self._ck(self.L.debwt_dev_partition_scatter_p2p(_p(items), _u64(items.numel()), _p(splitters), ctypes.c_uint32(n_split),
+                                                        _u64(mask), int(bool(drop_marker)), ctypes.c_uint32(n_ranks), dst, _p(ws),
+                                                        self._st()))
+
     def key_index(self, sorted_keys):
         n = sorted_keys.numel()
         bits = int(self.L.debwt_dev_key_index_bits(_u64(n)))
@@ -396,6 +409,86 @@ def special_tables_host(info_np, ins_by_t, seps_np, n_rec):
 
 
 # --------------------------------------------------------------------------------------------------
+# fused bucket + exchange over NVLink peer memory
+# --------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """zero-copy view of a raw device pointer for torch.as_tensor"""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """All-to-all of 64-bit items without a staging buffer: every rank exports a receive buffer through CUDA
+    IPC, the partition kernel stores each item straight into its owner's buffer (coalesced peer stores over
+    NVLink / NVSwitch), and a barrier closes the exchange.  Only the G x G count matrix goes through
+    torch.distributed.  Used for the key exchange and for the in-edge queries when the backend is NCCL."""
+
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, comm: "Comm", ops, name: str) -> "PeerExchange":
+        key = (id(comm), name)
+        if key not in cls._cache:
+            cls._cache[key] = PeerExchange(comm, ops)
+        return cls._cache[key]
+
+    def __init__(self, comm: "Comm", ops):
+        self.comm, self.ops, self.cap = comm, ops, 0
+        self.ptrs = [0] * comm.size
+
+    def _release(self):
+        L = self.ops.L
+        for r, p in enumerate(self.ptrs):
+            if not p:
+                continue
+            if r == self.comm.rank:
+                L.debwt_dev_ipc_free(ctypes.c_void_p(p))
+            else:
+                L.debwt_dev_ipc_close(ctypes.c_void_p(p))
+        self.ptrs = [0] * self.comm.size
+        self.cap = 0
+
+    def _ensure(self, need: int):
+        """collective: `need` is the same on every rank"""
+        if need <= self.cap:
+            return
+        torch.cuda.synchronize()
+        self.comm.barrier()                      # nobody is still writing into / reading from the old buffers
+        self._release()
+        cap = int(need * 1.25) + 4096
+        L = self.ops.L
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        binding.check(L.debwt_dev_ipc_alloc(ctypes.c_uint64(cap * 8), ctypes.byref(ptr), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8)
+        allh = self.comm.all_gather_equal(self.comm.to_coll(mine)).cpu().numpy()
+        for r in range(self.comm.size):
+            if r == self.comm.rank:
+                self.ptrs[r] = ptr.value
+            else:
+                h = (ctypes.c_ubyte * 64)(*allh[r * 64:(r + 1) * 64].tolist())
+                p = ctypes.c_void_p()
+                binding.check(L.debwt_dev_ipc_open(h, ctypes.byref(p)))
+                self.ptrs[r] = p.value
+        self.cap = cap
+
+    def exchange(self, items: torch.Tensor, d_split: torch.Tensor, n_split: int, drop_marker: bool) -> torch.Tensor:
+        comm, ops, G, me = self.comm, self.ops, self.comm.size, self.comm.rank
+        counts = ops.partition_count(items, d_split, n_split, 0xFFFFFFFFFFFFFFFC, drop_marker, G)
+        mat = comm.all_gather_equal(comm.to_coll(torch.tensor(counts, dtype=torch.int64))).cpu().view(G, G)   # [src][dst]
+        self._ensure(int(mat.sum(0).max()))
+        dst = (ctypes.c_void_p * G)(*[self.ptrs[d] + 8 * int(mat[:me, d].sum()) for d in range(G)])
+        ops.partition_scatter_p2p(items, d_split, n_split, 0xFFFFFFFFFFFFFFFC, drop_marker, G, dst)
+        torch.cuda.synchronize()
+        comm.barrier()                            # every peer has finished storing into this rank's buffer
+        comm.bytes_sent += int(mat[me].sum() - mat[me, me]) * 8
+        n_recv = int(mat[:, me].sum())
+        if n_recv == 0:
+            return items.new_empty(0)
+        return torch.as_tensor(_RawCuda(self.ptrs[me], n_recv), device=items.device)
+
+
+# --------------------------------------------------------------------------------------------------
 # host-side geometry
 # --------------------------------------------------------------------------------------------------
 def valid_windows_before(x: int, seps: np.ndarray) -> int:
@@ -494,15 +587,23 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     d_split = ops.from_numpy(splitters_np) if G > 1 else ops.zeros(1)
     n_split = G - 1
 
-    def route(items, drop_marker):
-        """items grouped by the owner of their k-mer (top 62 bits) + the per-owner counts"""
-        return ops.partition_by_splitters(items, d_split, n_split, 0xFFFFFFFFFFFFFFFC, drop_marker, G)
+    import os as _os
+    use_p2p = (G > 1 and isinstance(ops, CudaOps) and not comm.staged and comm.coll_device.type == "cuda"
+               and _os.environ.get("DEBWT_P2P", "1") != "0")
+
+    def exchange(items, drop_marker, name):
+        """every item goes to the owner of its k-mer (top 62 bits): fused bucket + peer stores over NVLink when
+        the ranks can map each other's memory, else bucket + all-to-all through torch.distributed"""
+        if use_p2p:
+            return PeerExchange.get(comm, ops, name).exchange(items, d_split, n_split, drop_marker)
+        part, counts = ops.partition_by_splitters(items, d_split, n_split, 0xFFFFFFFFFFFFFFFC, drop_marker, G)
+        got, _ = comm.all_to_all_v(part, counts)
+        return got
 
     tick('extract+splitters')
     # 3. one all-to-all: every key goes to the owner of its k-mer
-    part, counts = route(keys, False)
-    mine, _ = comm.all_to_all_v(part, counts)
-    del keys, part
+    mine = exchange(keys, False, "keys")
+    del keys
     tick('partition+alltoall')
     n_loc = int(mine.numel())
     sk = ops.sort(mine, True) if getattr(ops, "timed_main_sort", False) else ops.sort(mine)
@@ -518,16 +619,14 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     tick('c.index')
     q = ops.out_edges_queries(sk, gmask) if n_loc else ops.empty(0)
     tick('c.out_edges')
-    qpart, qcounts = route(q, True)
-    tick('c.partition')
-    qrecv, _ = comm.all_to_all_v(qpart, qcounts)
-    tick('c.alltoall')
+    qrecv = exchange(q, True, "queries")
+    tick('c.exchange')
     if n_loc:
         ops.apply_in_queries(sk, ki, gmask, qrecv)
         tick('c.apply')
         ops.heads_tails(words, d_seps, R, sk, ki, gmask)
         ops.propagate(sk, gmask)
-    del q, qpart, qrecv
+    del q, qrecv
     tick('c.propagate')
     bt = ops.branch_table(sk, gmask)
     tick('c.branch')

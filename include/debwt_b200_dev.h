@@ -48,6 +48,20 @@ int debwt_dev_partition(const void* d_a, const void* d_b, const void* d_dest_u8,
 int debwt_dev_partition_by_splitters(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
                                      int drop_marker, uint32_t n_ranks, void* d_out, uint64_t* counts_out, void* d_workspace,
                                      void* stream);
+/* ---- fused bucket + exchange over NVLink peer memory --------------------------------------------
+   Receive buffers are plain cudaMalloc allocations exported through CUDA IPC; every rank opens the
+   buffers of its peers once.  A key exchange is then: count (below), all-gather of the counts (host),
+   one scatter kernel that stores every item directly into its owner's receive buffer, barrier. */
+int debwt_dev_ipc_alloc(uint64_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int debwt_dev_ipc_open(const unsigned char handle[64], void** d_ptr);
+int debwt_dev_ipc_close(void* d_ptr);
+int debwt_dev_ipc_free(void* d_ptr);
+/* counts_out[r] = items owned by rank r (host array of n_ranks); d_workspace: 128 bytes */
+int debwt_dev_partition_count(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
+                              int drop_marker, uint32_t n_ranks, uint64_t* counts_out, void* d_workspace, void* stream);
+/* dst[r] (host array of n_ranks device pointers): start of this rank's slot in rank r's receive buffer */
+int debwt_dev_partition_scatter_p2p(const void* d_items, uint64_t n, const void* d_splitters, uint32_t n_split, uint64_t mask,
+                                    int drop_marker, uint32_t n_ranks, void* const* dst, void* d_workspace, void* stream);
 /* direct index over sorted keys */
 int debwt_dev_key_index_bits(uint64_t n);
 int debwt_dev_key_index(const void* d_sorted, uint64_t n, void* d_idx_u32, int bits, void* stream);
