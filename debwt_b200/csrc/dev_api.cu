@@ -38,6 +38,15 @@ inline BranchTable BT(const void* kmer, const void* head, const void* blue, void
 
 extern "C" {
 
+int debwt_dev_init(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    cudaMemPool_t mp;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, device));
+    unsigned long long thr = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
+    return 0;
+}
+
 int debwt_dev_pack(const void* d_ascii, uint64_t n, void* d_words, uint64_t nwords, void* d_err, void* stream) {
     return k_pack_words(P8(d_ascii), n, P64(d_words), nwords, P32(d_err), S(stream));
 }

@@ -170,6 +170,7 @@ class CudaOps:
         self.L = _dev_lib()
         self.sort_cfg = sort_cfg
         self.launches = 0
+        binding.check(self.L.debwt_dev_init(device))
 
     # -- helpers --
     def _st(self):

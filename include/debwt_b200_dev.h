@@ -18,6 +18,10 @@
 extern "C" {
 #endif
 
+/* once per process and device: keeps the driver's stream-ordered pool from returning memory at every sync
+   (K10 takes its round scratch from it) */
+int debwt_dev_init(int device);
+
 /* K1 on a text slice: n ASCII symbols -> nwords packed words (T padding for [n, n+32), zeros beyond);
    *d_err (u32, device) is OR-ed with 1 on a non-ACGT symbol (src/collect#$.c:66-90). */
 int debwt_dev_pack(const void* d_ascii, uint64_t n, void* d_words, uint64_t nwords, void* d_err, void* stream);
