@@ -336,9 +336,132 @@ __global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u
     items[i] = w;
 }
 
+// Work lists of one round.  `small` items (<= CHUNK entries) are sorted in shared memory by refine_kernel; `huge`
+// items are first cut into small ones by split_kernel.  Counters live in device memory (cnt[0] small, cnt[1] huge).
+struct WorkLists {
+    WorkItem* small;
+    WorkItem* huge;
+    u32* cnt;
+    u32 cap_small, cap_huge;
+};
+
+__device__ __forceinline__ void push_item(const WorkLists& l, const WorkItem& w) {
+    if (w.len > (u32)CHUNK) {
+        const u32 i = atomicAdd(l.cnt + 1, 1u);
+        if (i < l.cap_huge) l.huge[i] = w;
+    } else {
+        const u32 i = atomicAdd(l.cnt + 0, 1u);
+        if (i < l.cap_small) l.small[i] = w;
+    }
+}
+
+// Sample-sort partition of the huge items (one block per item): up to 128 buckets delimited by splitters drawn
+// from the item's own code words at `depth` (8x oversampled), with a separate bucket for "equal to a splitter"
+// so that heavy ties -- the copies of a repeat family that agree on all 32 codes -- never unbalance a bucket.
+// Entries are moved bucket by bucket (through `scratch`), every bucket becomes an item of its own: ordinary
+// buckets at the same depth (sorted by refine_kernel this round when they fit CHUNK, split again next round
+// otherwise), equality buckets at depth + 32.  O(len) traffic per item instead of the O(len log^2 len) of a
+// sorting network over HBM.  Items holding a word with a separator code are left to refine_kernel's comparator
+// fallback (at most 32 R such entries exist).
+constexpr int SPLIT_MAX_BUCKETS = 128;
+constexpr int SPLIT_OVERSAMPLE = 8;
+constexpr int SPLIT_TARGET = 512;      // aimed-for bucket size
+
+__global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
+                                                       u32 n_items, WorkLists cur, WorkLists next,
+                                                       u64* __restrict__ scratch, u32* __restrict__ g_bucket) {
+    __shared__ u64 s_sample[SPLIT_MAX_BUCKETS * SPLIT_OVERSAMPLE];
+    __shared__ u64 s_split[SPLIT_MAX_BUCKETS];
+    __shared__ u32 s_hist[2 * SPLIT_MAX_BUCKETS], s_start[2 * SPLIT_MAX_BUCKETS], s_pos[2 * SPLIT_MAX_BUCKETS];
+    __shared__ int s_flag, s_mixed;
+    for (u32 idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+        const WorkItem it = items[idx];
+        const u32 len = it.len, depth = it.depth;
+        u64* ent = blue + it.off;
+        u32 nb = (len + SPLIT_TARGET - 1) / SPLIT_TARGET;
+        if (nb > (u32)SPLIT_MAX_BUCKETS) nb = SPLIT_MAX_BUCKETS;
+        if (nb < 2) nb = 2;
+        const u32 m = nb * SPLIT_OVERSAMPLE, P = pow2_at_least(m), n_split = nb - 1, n_buckets = 2 * nb - 1;
+        if (threadIdx.x == 0) { s_flag = 0; s_mixed = 0; }
+        for (u32 t = threadIdx.x; t < 2u * SPLIT_MAX_BUCKETS; t += blockDim.x) s_hist[t] = 0;
+        // ---- sample, sort the sample, keep every SPLIT_OVERSAMPLE-th word as a splitter ----
+        for (u32 t = threadIdx.x; t < P; t += blockDim.x) {
+            u64 wd = ~0ull;
+            if (t < m) {
+                const u64 e = ent[(u64)t * len / m];
+                wd = text_window32(sp.codes, (e >> 4) + depth);
+            }
+            s_sample[t] = wd;
+        }
+        __syncthreads();
+        for (u32 k = 2; k <= P; k <<= 1) {
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                    const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const u64 a = s_sample[i], b = s_sample[l];
+                    if ((a > b) == ((i & k) == 0)) { s_sample[i] = b; s_sample[l] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (u32 t = threadIdx.x; t < n_split; t += blockDim.x) s_split[t] = s_sample[t * SPLIT_OVERSAMPLE + SPLIT_OVERSAMPLE - 1];
+        __syncthreads();
+        // ---- pass 1: bucket of every entry, histogram ----
+        const u32 prev0 = (u32)(ent[0] & 15ull);
+        for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+            const u64 e = ent[t];
+            if ((u32)(e & 15ull) != prev0) s_mixed = 1;
+            const u64 sidx = (e >> 4) + depth;
+            const u64 wd = text_window32(sp.codes, sidx);
+            if (!(fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes)) s_flag = 1;
+            u32 lo = 0, hi = n_split;                       // first splitter >= wd
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                if (s_split[mid] < wd) lo = mid + 1; else hi = mid;
+            }
+            const u32 b = 2 * lo + ((lo < n_split && s_split[lo] == wd) ? 1u : 0u);
+            atomicAdd(&s_hist[b], 1u);
+            g_bucket[it.off + t] = b;
+        }
+        __syncthreads();
+        const bool fallback = s_flag != 0, mixed = s_mixed != 0;
+        if (!mixed) { __syncthreads(); continue; }          // every prev symbol equal: nothing to order
+        if (fallback) {                                     // separator inside a word: comparator path of refine_kernel
+            if (threadIdx.x == 0) {
+                const u32 i = atomicAdd(cur.cnt + 0, 1u);
+                if (i < cur.cap_small) cur.small[i] = it;
+            }
+            __syncthreads();
+            continue;
+        }
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (u32 b = 0; b < n_buckets; ++b) { s_start[b] = run; s_pos[b] = run; run += s_hist[b]; }
+        }
+        __syncthreads();
+        // ---- pass 2: move the entries bucket by bucket ----
+        for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
+            const u32 b = g_bucket[it.off + t];
+            scratch[it.off + atomicAdd(&s_pos[b], 1u)] = ent[t];
+        }
+        __syncthreads();
+        for (u32 t = threadIdx.x; t < len; t += blockDim.x) ent[t] = scratch[it.off + t];
+        // ---- every bucket with two or more entries is an item ----
+        for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) {
+            const u32 c = s_hist[b];
+            if (c < 2) continue;
+            WorkItem nw;
+            nw.off = it.off + s_start[b]; nw.len = c; nw.depth = depth + ((b & 1u) ? 32u : 0u);
+            push_item(c > (u32)CHUNK ? next : cur, nw);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(BIG_TPB) refine_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
-                                                        u32 n_items, WorkItem* __restrict__ next, u32* __restrict__ next_count,
+                                                        const u32* __restrict__ n_items_ptr, WorkLists next,
                                                         u64* __restrict__ g_key, u32* __restrict__ g_tag) {
+    const u32 n_items = *n_items_ptr;
     extern __shared__ __align__(16) unsigned char blk_smem[];
     SegArrays s;
     s.ent = reinterpret_cast<u64*>(blk_smem);
@@ -412,7 +535,7 @@ __global__ void __launch_bounds__(BIG_TPB) refine_kernel(u64* __restrict__ blue,
                     if (size > 32) {
                         WorkItem nw;
                         nw.off = it.off + h; nw.len = size; nw.depth = depth + 32;
-                        next[atomicAdd(next_count, 1u)] = nw;
+                        push_item(next, nw);
                     }
                 }
             }
@@ -462,37 +585,48 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
     auto blocks_for = [](u32 warps) { u32 b = (warps + WARPS - 1) / WARPS; return b > 148u * 16u ? 148u * 16u : (b ? b : 1u); };
     if (h[0]) { sort_small_kernel<<<blocks_for(h[0]), TPB, 0, st>>>(blue, bt, sp, small, counts + 0); ++launched; }
     if (h[1]) { sort_mid_kernel<<<blocks_for(h[1]), TPB, 0, st>>>(blue, bt, sp, mid, counts + 1); ++launched; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
-        attr_done = true;
-    }
     const u32 n_big = h[2] + h[3];
     if (n_big) {
         // round-based refinement of the segments beyond one warp's shared-memory slice
-        const u64 cap = bt.n_blue / 32 + n_big + 16;
+        static bool attr_done = false;
+        if (!attr_done) {
+            CUDA_TRY(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
+            attr_done = true;
+        }
+        const u64 cap_small64 = bt.n_blue / 16 + n_big + 16, cap_huge64 = bt.n_blue / CHUNK + h[3] + 16;
+        if (cap_small64 > 0xffffffffull) { set_error("internal: K10 work list too large"); return -1; }
+        const u32 cap_small = (u32)cap_small64, cap_huge = (u32)cap_huge64;
         WorkItem* lists = nullptr;
         u32* d_cnt = nullptr;
         u64* g_key = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lists), 2 * cap * sizeof(WorkItem), st));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lists), 2 * ((u64)cap_small + cap_huge) * sizeof(WorkItem), st));
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), 64, st));
         if (h[3]) CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_key), bt.n_blue * 12 + 64, st));
         u32* g_tag = g_key ? reinterpret_cast<u32*>(g_key + bt.n_blue) : nullptr;
-        WorkItem* cur = lists;
-        WorkItem* nxt = lists + cap;
-        if (h[2]) seed_items_kernel<<<(h[2] + TPB - 1) / TPB, TPB, 0, st>>>(bt, block, h[2], cur);
-        if (h[3]) seed_items_kernel<<<(h[3] + TPB - 1) / TPB, TPB, 0, st>>>(bt, huge, h[3], cur + h[2]);
+        WorkLists cur{lists, lists + cap_small, d_cnt, cap_small, cap_huge};
+        WorkLists nxt{lists + cap_small + cap_huge, lists + 2 * (u64)cap_small + cap_huge, d_cnt + 2, cap_small, cap_huge};
+        if (h[2]) seed_items_kernel<<<(h[2] + TPB - 1) / TPB, TPB, 0, st>>>(bt, block, h[2], cur.small);
+        if (h[3]) seed_items_kernel<<<(h[3] + TPB - 1) / TPB, TPB, 0, st>>>(bt, huge, h[3], cur.huge);
         launched += (h[2] ? 1 : 0) + (h[3] ? 1 : 0);
-        u32 n_items = n_big;
-        for (int round = 0; n_items && round < 100000; ++round) {
-            CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, st));
-            refine_kernel<<<n_items < 148u * 2u ? n_items : 148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, sp, cur, n_items, nxt, d_cnt,
-                                                                                                    g_key, g_tag);
+        u32 n_cur[2] = {h[2], h[3]};
+        CUDA_TRY(cudaMemcpyAsync(cur.cnt, n_cur, 8, cudaMemcpyHostToDevice, st));
+        const u32 grid = 148u * 2u;
+        for (int round = 0; (n_cur[0] || n_cur[1]) && round < 100000; ++round) {
+            CUDA_TRY(cudaMemsetAsync(nxt.cnt, 0, 8, st));
+            if (n_cur[1]) {
+                split_kernel<<<n_cur[1] < grid ? n_cur[1] : grid, BIG_TPB, 0, st>>>(blue, sp, cur.huge, n_cur[1], cur, nxt, g_key, g_tag);
+                ++launched;
+            }
+            refine_kernel<<<grid, BIG_TPB, kChunkSmem, st>>>(blue, sp, cur.small, cur.cnt, nxt, g_key, g_tag);
             ++launched;
-            CUDA_TRY(cudaMemcpyAsync(&n_items, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+            u32 n_fin[4];
+            CUDA_TRY(cudaMemcpyAsync(n_fin, d_cnt, 16, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            if (n_items > cap) { set_error("internal: K10 work list overflow"); return -1; }
-            WorkItem* t = cur; cur = nxt; nxt = t;
+            const u32* c = cur.cnt == d_cnt ? n_fin : n_fin + 2;
+            const u32* n = cur.cnt == d_cnt ? n_fin + 2 : n_fin;
+            if (c[0] > cap_small || n[0] > cap_small || n[1] > cap_huge) { set_error("internal: K10 work list overflow"); return -1; }
+            n_cur[0] = n[0]; n_cur[1] = n[1];
+            WorkLists t = cur; cur = nxt; nxt = t;
         }
         CUDA_TRY(cudaFreeAsync(lists, st));
         CUDA_TRY(cudaFreeAsync(d_cnt, st));

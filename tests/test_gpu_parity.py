@@ -192,9 +192,10 @@ def test_bwt_many_short_records(n_rec):
     assert all((a == b).all() for a, b in zip(want, got))
 
 
-@pytest.mark.parametrize("copies,el_len,muts", [(6000, 150, 4), (20000, 90, 3)])
+@pytest.mark.parametrize("copies,el_len,muts", [(6000, 150, 4), (20000, 90, 3), (30000, 64, 1), (9000, 400, 2)])
 def test_bwt_huge_segments_vs_oracle(copies, el_len, muts):
-    # segments beyond one shared-memory block (4096 entries): the multi-level chunked network over HBM
+    # segments beyond one shared-memory block (4096 entries): sample-sort split (tie-heavy with 1-2 mutations per
+    # copy) and, for items with a separator code inside a word, the chunked network over HBM
     rng = np.random.default_rng(copies)
     master = synth.random_bases(99, el_len)
     parts = []

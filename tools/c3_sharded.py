@@ -9,7 +9,7 @@ rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n, nrec = int(float(sys.argv[1])), int(sys.argv[2])
-t0 = time.time(); recs = synth.config3(n, nrec); tg = time.time() - t0
+t0 = time.time(); recs = synth.config4(n // nrec, nrec) if os.environ.get('DEBWT_CFG') == 'c4' else synth.config3(n, nrec); tg = time.time() - t0
 text, seps = api.join_records(recs)
 del recs
 comm, ops = D.Comm(), D.CudaOps(local)

@@ -2,17 +2,17 @@
   python tools/c3_validate.py <n_bases> <n_records> [invert]
 Builds the BWT, prints per-phase stats and the SHA-256 of the packed words; with `invert`, rebuilds the
 text from the BWT by LF-walk (oracle) and compares it with the input (size-independent property)."""
-import hashlib, json, sys, time
+import hashlib, json, os, sys, time
 sys.path.insert(0, ".")
 import numpy as np
 from debwt_b200 import api, synth
 
 n, nrec = int(float(sys.argv[1])), int(sys.argv[2])
 invert = len(sys.argv) > 3 and sys.argv[3] == "invert"
-t0 = time.time(); recs = synth.config3(n, nrec); tg = time.time() - t0
+t0 = time.time(); recs = synth.config4(n // nrec, nrec) if os.environ.get('DEBWT_CFG') == 'c4' else synth.config3(n, nrec); tg = time.time() - t0
 print(f"generated {sum(r.size for r in recs)} bases in {len(recs)} records in {tg:.1f} s", flush=True)
 with api.BwtBuilder() as b:
-    for rep in range(2):
+    for rep in range(int(os.environ.get("DEBWT_REPS", "2"))):
         t0 = time.time(); b.set_records(recs); b.build(); w, s, d = b.result(); wall = time.time() - t0
     st = b.stats()
 st["wall_s"] = wall
