@@ -22,6 +22,9 @@
 // (src/sortBlue.c:192-219): any order gives the same BWT.
 #include "stages.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace debwt {
 
 namespace {
@@ -219,9 +222,13 @@ struct SegArrays {
 template <typename Less>
 __device__ __forceinline__ void cmpswap3(const SegArrays& a, u32 i, u32 l, const Less& less) {
     const u64 ei = a.ent[i], el = a.ent[l], ki = a.key[i], kl = a.key[l];
-    const u32 ti = a.tag[i], tl = a.tag[l];
-    if (less(el, kl, tl, ei, ki, ti)) {
-        a.ent[i] = el; a.ent[l] = ei; a.key[i] = kl; a.key[l] = ki; a.tag[i] = tl; a.tag[l] = ti;
+    if constexpr (Less::kUsesTag) {
+        const u32 ti = a.tag[i], tl = a.tag[l];
+        if (less(el, kl, tl, ei, ki, ti)) {
+            a.ent[i] = el; a.ent[l] = ei; a.key[i] = kl; a.key[l] = ki; a.tag[i] = tl; a.tag[l] = ti;
+        }
+    } else {                                            // tags carry nothing the order depends on: leave them
+        if (less(el, kl, 0u, ei, ki, 0u)) { a.ent[i] = el; a.ent[l] = ei; a.key[i] = kl; a.key[l] = ki; }
     }
 }
 
@@ -257,16 +264,16 @@ __device__ __forceinline__ u32 pow2_at_least(u32 n) {
     return p;
 }
 
-// full network over `len` entries in `g` (HBM when len > CHUNK), staging through `s`
-template <typename Less>
+// full network over `len` entries in `g` (HBM when len > CH), staging through `s`
+template <int CH, typename Less>
 __device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool in_smem, const Less& less) {
     if (in_smem) {                                  // the segment already sits in `s`
         net_local(s, len, 2, pow2_at_least(len), false, less);
         return;
     }
     const u32 P = pow2_at_least(len);
-    for (u32 k = CHUNK; k <= P; k <<= 1) {
-        if (k > CHUNK) {                            // stages with partner distance >= CHUNK run over HBM
+    for (u32 k = CH; k <= P; k <<= 1) {
+        if (k > CH) {                            // stages with partner distance >= CH run over HBM
             const u32 half = k >> 1;
             for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
                 const u32 i = ((t & ~(half - 1)) << 1) | (t & (half - 1));
@@ -274,7 +281,7 @@ __device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool i
                 if (l < len) cmpswap3(g, i, l, less);
             }
             __syncthreads();
-            for (u32 j = k >> 2; j >= (u32)CHUNK; j >>= 1) {
+            for (u32 j = k >> 2; j >= (u32)CH; j >>= 1) {
                 for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
                     const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const u32 l = i | j;
@@ -283,14 +290,14 @@ __device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool i
                 __syncthreads();
             }
         }
-        for (u32 c0 = 0; c0 < len; c0 += CHUNK) {   // the remaining stages block by block in shared memory
-            const u32 clen = (len - c0 < (u32)CHUNK) ? len - c0 : (u32)CHUNK;
+        for (u32 c0 = 0; c0 < len; c0 += CH) {   // the remaining stages block by block in shared memory
+            const u32 clen = (len - c0 < (u32)CH) ? len - c0 : (u32)CH;
             for (u32 t = threadIdx.x; t < clen; t += blockDim.x) {
                 s.ent[t] = g.ent[c0 + t]; s.key[t] = g.key[c0 + t]; s.tag[t] = g.tag[c0 + t];
             }
             __syncthreads();
-            if (k == (u32)CHUNK) net_local(s, clen, 2, pow2_at_least(clen), false, less);
-            else net_local(s, clen, CHUNK, CHUNK, true, less);
+            if (k == (u32)CH) net_local(s, clen, 2, pow2_at_least(clen), false, less);
+            else net_local(s, clen, CH, CH, true, less);
             for (u32 t = threadIdx.x; t < clen; t += blockDim.x) {
                 g.ent[c0 + t] = s.ent[t]; g.key[c0 + t] = s.key[t]; g.tag[c0 + t] = s.tag[t];
             }
@@ -300,10 +307,12 @@ __device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool i
 }
 
 struct LessKey {
+    static constexpr bool kUsesTag = false;
     __device__ __forceinline__ bool operator()(u64, u64 ka, u32, u64, u64 kb, u32) const { return ka < kb; }
 };
 // comparator for items whose code words contain a separator: words at `depth` are cached in key (tag = plain)
 struct LessFromDepth {
+    static constexpr bool kUsesTag = true;
     SpView sp;
     u32 depth;
     __device__ __forceinline__ bool operator()(u64 ea, u64 ka, u32 ta, u64 eb, u64 kb, u32 tb) const {
@@ -324,8 +333,34 @@ struct WorkItem {
     u32 len, depth;
 };
 
-__global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u32* __restrict__ list, u32 n,
-                                                        WorkItem* __restrict__ items) {
+// Work lists of one round, by item size: `tiny` (<= TINY entries: 128-thread blocks, many per SM -- the per-item cost
+// is barrier latency, so what counts is the number of items in flight), `small` (<= CHUNK: one 512-thread block,
+// whole item in shared memory), `huge` (first cut into tiny/small ones by split_kernel).  Counters live in
+// device memory: cnt[0] small, cnt[1] huge, cnt[2] tiny.
+constexpr int TINY = 512;
+constexpr int TINY_TPB = 128;
+struct WorkLists {
+    WorkItem* small;
+    WorkItem* huge;
+    WorkItem* tiny;
+    u32* cnt;
+    u32 cap_small, cap_huge, cap_tiny;
+};
+
+__device__ __forceinline__ void push_item(const WorkLists& l, const WorkItem& w) {
+    if (w.len > (u32)CHUNK) {
+        const u32 i = atomicAdd(l.cnt + 1, 1u);
+        if (i < l.cap_huge) l.huge[i] = w;
+    } else if (w.len > (u32)TINY) {
+        const u32 i = atomicAdd(l.cnt + 0, 1u);
+        if (i < l.cap_small) l.small[i] = w;
+    } else {
+        const u32 i = atomicAdd(l.cnt + 2, 1u);
+        if (i < l.cap_tiny) l.tiny[i] = w;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u32* __restrict__ list, u32 n, WorkLists cur) {
     const u32 i = blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     const u32 b = list[i];
@@ -333,26 +368,7 @@ __global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u
     w.off = bt.blue[b];
     w.len = bt.blue[b + 1] - bt.blue[b];
     w.depth = 0;
-    items[i] = w;
-}
-
-// Work lists of one round.  `small` items (<= CHUNK entries) are sorted in shared memory by refine_kernel; `huge`
-// items are first cut into small ones by split_kernel.  Counters live in device memory (cnt[0] small, cnt[1] huge).
-struct WorkLists {
-    WorkItem* small;
-    WorkItem* huge;
-    u32* cnt;
-    u32 cap_small, cap_huge;
-};
-
-__device__ __forceinline__ void push_item(const WorkLists& l, const WorkItem& w) {
-    if (w.len > (u32)CHUNK) {
-        const u32 i = atomicAdd(l.cnt + 1, 1u);
-        if (i < l.cap_huge) l.huge[i] = w;
-    } else {
-        const u32 i = atomicAdd(l.cnt + 0, 1u);
-        if (i < l.cap_small) l.small[i] = w;
-    }
+    push_item(cur, w);
 }
 
 // Sample-sort partition of the huge items (one block per item): up to 128 buckets delimited by splitters drawn
@@ -363,9 +379,9 @@ __device__ __forceinline__ void push_item(const WorkLists& l, const WorkItem& w)
 // otherwise), equality buckets at depth + 32.  O(len) traffic per item instead of the O(len log^2 len) of a
 // sorting network over HBM.  Items holding a word with a separator code are left to refine_kernel's comparator
 // fallback (at most 32 R such entries exist).
-constexpr int SPLIT_MAX_BUCKETS = 128;
+constexpr int SPLIT_MAX_BUCKETS = 256;
 constexpr int SPLIT_OVERSAMPLE = 8;
-constexpr int SPLIT_TARGET = 512;      // aimed-for bucket size
+constexpr int SPLIT_TARGET = 256;      // aimed-for bucket size (the tiny class)
 
 __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
                                                        u32 n_items, WorkLists cur, WorkLists next,
@@ -458,20 +474,21 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
     }
 }
 
-__global__ void __launch_bounds__(BIG_TPB) refine_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
-                                                        const u32* __restrict__ n_items_ptr, WorkLists next,
+template <int NT, int CH, int MINB>
+__global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
+                                                         const u32* __restrict__ n_items_ptr, WorkLists next,
                                                         u64* __restrict__ g_key, u32* __restrict__ g_tag) {
     const u32 n_items = *n_items_ptr;
     extern __shared__ __align__(16) unsigned char blk_smem[];
     SegArrays s;
     s.ent = reinterpret_cast<u64*>(blk_smem);
-    s.key = s.ent + CHUNK;
-    s.tag = reinterpret_cast<u32*>(s.key + CHUNK);
+    s.key = s.ent + CH;
+    s.tag = reinterpret_cast<u32*>(s.key + CH);
     __shared__ int s_flag, s_mixed;
     for (u32 idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
         const WorkItem it = items[idx];
         const u32 len = it.len, depth = it.depth;
-        const bool in_hbm = len > (u32)CHUNK;
+        const bool in_hbm = len > (u32)CH;
         SegArrays g;
         g.ent = blue + it.off;
         g.key = in_hbm ? g_key + it.off : s.key;
@@ -498,9 +515,9 @@ __global__ void __launch_bounds__(BIG_TPB) refine_kernel(u64* __restrict__ blue,
             // every prev symbol equal: any order gives the same BWT (src/sortBlue.c:192-219)
         } else if (fallback) {
             LessFromDepth lf{sp, depth};
-            net_sort(g, s, len, !in_hbm, lf);           // final order for this item
+            net_sort<CH>(g, s, len, !in_hbm, lf);           // final order for this item
         } else {
-            net_sort(g, s, len, !in_hbm, LessKey());
+            net_sort<CH>(g, s, len, !in_hbm, LessKey());
             // ---- runs of equal words: head index of every entry (max-scan over "own index if head") ----
             for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = (t == 0 || w.key[t] != w.key[t - 1]) ? 1u : 0u;
             __syncthreads();
@@ -547,11 +564,27 @@ __global__ void __launch_bounds__(BIG_TPB) refine_kernel(u64* __restrict__ blue,
                 const u32 size = __popc(__ballot_sync(0xffffffffu, mem));
                 if (h + 32 < len && w.tag[h + 32] == h) continue;                      // long run: next round
                 const u64 e = mem ? w.ent[h + lane] : 0;
+                // every lane fetches its next word once; the pairwise comparisons then run on registers and only
+                // walk the code strings when two next words tie as well
+                u64 nw = 0;
+                u32 np = 0;
+                if (mem) {
+                    const u64 sidx = (e >> 4) + depth + 32;
+                    nw = text_window32(sp.codes, sidx);
+                    np = (fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
+                }
                 u32 rank = 0;
                 for (u32 j = 0; j < size; ++j) {
                     __syncwarp();
                     const u64 ej = __shfl_sync(0xffffffffu, e, j);
-                    if (mem && j != lane && sp_less_from(sp, ej >> 4, e >> 4, depth + 32)) ++rank;
+                    const u64 wj = __shfl_sync(0xffffffffu, nw, j);
+                    const u32 pj = __shfl_sync(0xffffffffu, np, j);
+                    if (mem && j != lane) {
+                        bool less;
+                        if (pj && np) less = wj != nw ? wj < nw : sp_less_from(sp, ej >> 4, e >> 4, depth + 64);
+                        else less = sp_less_from(sp, ej >> 4, e >> 4, depth + 32);
+                        if (less) ++rank;
+                    }
                 }
                 __syncwarp();
                 if (mem) w.ent[h + rank] = e;
@@ -588,44 +621,56 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
     const u32 n_big = h[2] + h[3];
     if (n_big) {
         // round-based refinement of the segments beyond one warp's shared-memory slice
+        auto refine_small = refine_kernel<BIG_TPB, CHUNK, 2>;
+        auto refine_tiny = refine_kernel<TINY_TPB, TINY, 8>;    // 8, 10 or 12 blocks per SM measured the same
         static bool attr_done = false;
         if (!attr_done) {
-            CUDA_TRY(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
+            CUDA_TRY(cudaFuncSetAttribute(refine_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
             attr_done = true;
         }
-        const u64 cap_small64 = bt.n_blue / 16 + n_big + 16, cap_huge64 = bt.n_blue / CHUNK + h[3] + 16;
-        if (cap_small64 > 0xffffffffull) { set_error("internal: K10 work list too large"); return -1; }
-        const u32 cap_small = (u32)cap_small64, cap_huge = (u32)cap_huge64;
+        const u64 cap_tiny64 = bt.n_blue / 16 + n_big + 16, cap_huge64 = bt.n_blue / CHUNK + h[3] + 16;
+        const u64 cap_small64 = bt.n_blue / TINY + cap_huge64 + 16;
+        if (cap_tiny64 > 0xffffffffull) { set_error("internal: K10 work list too large"); return -1; }
+        const u32 cap_tiny = (u32)cap_tiny64, cap_small = (u32)cap_small64, cap_huge = (u32)cap_huge64;
+        const u64 per_set = (u64)cap_tiny + cap_small + cap_huge;
         WorkItem* lists = nullptr;
         u32* d_cnt = nullptr;
         u64* g_key = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lists), 2 * ((u64)cap_small + cap_huge) * sizeof(WorkItem), st));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lists), 2 * per_set * sizeof(WorkItem), st));
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), 64, st));
         if (h[3]) CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_key), bt.n_blue * 12 + 64, st));
         u32* g_tag = g_key ? reinterpret_cast<u32*>(g_key + bt.n_blue) : nullptr;
-        WorkLists cur{lists, lists + cap_small, d_cnt, cap_small, cap_huge};
-        WorkLists nxt{lists + cap_small + cap_huge, lists + 2 * (u64)cap_small + cap_huge, d_cnt + 2, cap_small, cap_huge};
-        if (h[2]) seed_items_kernel<<<(h[2] + TPB - 1) / TPB, TPB, 0, st>>>(bt, block, h[2], cur.small);
-        if (h[3]) seed_items_kernel<<<(h[3] + TPB - 1) / TPB, TPB, 0, st>>>(bt, huge, h[3], cur.huge);
+        WorkLists cur{lists, lists + cap_small, lists + cap_small + cap_huge, d_cnt, cap_small, cap_huge, cap_tiny};
+        WorkLists nxt{lists + per_set, lists + per_set + cap_small, lists + per_set + cap_small + cap_huge, d_cnt + 4,
+                      cap_small, cap_huge, cap_tiny};
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 32, st));
+        if (h[2]) seed_items_kernel<<<(h[2] + TPB - 1) / TPB, TPB, 0, st>>>(bt, block, h[2], cur);
+        if (h[3]) seed_items_kernel<<<(h[3] + TPB - 1) / TPB, TPB, 0, st>>>(bt, huge, h[3], cur);
         launched += (h[2] ? 1 : 0) + (h[3] ? 1 : 0);
-        u32 n_cur[2] = {h[2], h[3]};
-        CUDA_TRY(cudaMemcpyAsync(cur.cnt, n_cur, 8, cudaMemcpyHostToDevice, st));
-        const u32 grid = 148u * 2u;
-        for (int round = 0; (n_cur[0] || n_cur[1]) && round < 100000; ++round) {
-            CUDA_TRY(cudaMemsetAsync(nxt.cnt, 0, 8, st));
+        u32 n_cur[3] = {1, h[3], 1};                      // exact small/tiny counts are on the device
+        for (int round = 0; (n_cur[0] || n_cur[1] || n_cur[2]) && round < 100000; ++round) {
+            CUDA_TRY(cudaMemsetAsync(nxt.cnt, 0, 16, st));
             if (n_cur[1]) {
+                const u32 grid = 148u * 2u;
                 split_kernel<<<n_cur[1] < grid ? n_cur[1] : grid, BIG_TPB, 0, st>>>(blue, sp, cur.huge, n_cur[1], cur, nxt, g_key, g_tag);
                 ++launched;
             }
-            refine_kernel<<<grid, BIG_TPB, kChunkSmem, st>>>(blue, sp, cur.small, cur.cnt, nxt, g_key, g_tag);
-            ++launched;
-            u32 n_fin[4];
-            CUDA_TRY(cudaMemcpyAsync(n_fin, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+            refine_small<<<148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, sp, cur.small, cur.cnt + 0, nxt, g_key, g_tag);
+            refine_tiny<<<148u * 8u, TINY_TPB, (size_t)TINY * 20, st>>>(blue, sp, cur.tiny, cur.cnt + 2, nxt, g_key, g_tag);
+            launched += 2;
+            u32 n_fin[8];
+            CUDA_TRY(cudaMemcpyAsync(n_fin, d_cnt, 32, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            const u32* c = cur.cnt == d_cnt ? n_fin : n_fin + 2;
-            const u32* n = cur.cnt == d_cnt ? n_fin + 2 : n_fin;
-            if (c[0] > cap_small || n[0] > cap_small || n[1] > cap_huge) { set_error("internal: K10 work list overflow"); return -1; }
-            n_cur[0] = n[0]; n_cur[1] = n[1];
+            const u32* c = cur.cnt == d_cnt ? n_fin : n_fin + 4;
+            const u32* n = cur.cnt == d_cnt ? n_fin + 4 : n_fin;
+            if (c[0] > cap_small || c[2] > cap_tiny || n[0] > cap_small || n[1] > cap_huge || n[2] > cap_tiny) {
+                set_error("internal: K10 work list overflow");
+                return -1;
+            }
+            if (getenv("DEBWT_K10_DEBUG"))
+                fprintf(stderr, "K10 round %d: small %u tiny %u (huge split %u) -> next small %u huge %u tiny %u\n", round, c[0], c[2],
+                        n_cur[1], n[0], n[1], n[2]);
+            n_cur[0] = n[0]; n_cur[1] = n[1]; n_cur[2] = n[2];
             WorkLists t = cur; cur = nxt; nxt = t;
         }
         CUDA_TRY(cudaFreeAsync(lists, st));
