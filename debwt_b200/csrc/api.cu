@@ -377,7 +377,14 @@ int debwt_build(debwt_ctx* c, int k) {
     ws.ev_sweep_begin = c->ev[11]; ws.ev_sweep_end = c->ev[12]; ws.sweeps_out = &sweeps;
     const unsigned launches_before_sort = g_launches;
     u64* d_keys = nullptr;
-    if (radix_sort_u64(d_ka, d_kb, nk, ws, st, &d_keys)) return -1;
+    KeyIndex ki;                        // direct index over the sorted keys: marked by the last sort pass
+    ki.bits = key_index_bits(nk);
+    if (dalloc(pool, &ki.idx, (1ull << ki.bits) + 2) || k_key_index_init(ki, st)) return -1;
+    bool index_marked = false;
+    ws.key_index = ki.idx; ws.key_index_bits = ki.bits; ws.key_index_done = &index_marked;
+    const bool text_hist = text_digit_hist_applies(n, R);
+    if (text_hist && (radix_sort_clear(ws, st) || k_text_digit_hist(d_text, n, d_seps, R, ws.hist, st))) return -1;
+    if (radix_sort_u64(d_ka, d_kb, nk, ws, st, &d_keys, text_hist)) return -1;
     S.sort_launches = g_launches - launches_before_sort;
     S.sort_sweeps = (u32)sweeps;
     pool.release(d_sortws);
@@ -390,10 +397,7 @@ int debwt_build(debwt_ctx* c, int k) {
     u16* d_gmask = nullptr;
     if (dalloc(pool, &d_gmask, nk + 2)) return -1;
     CUDA_TRY(cudaMemsetAsync(d_gmask, 0, (nk + 2) * 2, st));
-    KeyIndex ki;
-    ki.bits = key_index_bits(nk);
-    if (dalloc(pool, &ki.idx, (1ull << ki.bits) + 2)) return -1;
-    if (k_build_key_index(d_keys, nk, ki, st)) return -1;
+    if (k_key_index_finish(d_keys, nk, ki, index_marked, st)) return -1;
     if (k_mark_edges(d_keys, nk, ki, d_gmask, st)) return -1;
     if (k_mark_heads_tails(d_text, d_seps, R, d_keys, nk, ki, d_gmask, st)) return -1;
     void* d_brws = nullptr; u64* d_tot = nullptr;

@@ -134,7 +134,7 @@ __device__ __forceinline__ u32 match_digit(u32 d) {
 template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 ntiles, const u64* __restrict__ gbase,
-                u64* __restrict__ lookback, u32* __restrict__ tile_counter, u64 epoch) {
+                u64* __restrict__ lookback, u32* __restrict__ tile_counter, u64 epoch, u32* __restrict__ kidx, int kshift) {
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * ITEMS;
     static_assert(THREADS >= RADIX, "one thread per digit is assumed");
@@ -286,17 +286,33 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 nt
         __syncthreads();
 
         // ---- write out: consecutive threads -> consecutive addresses inside a bin ----
+        // The last pass leaves the keys in their final order, and the keys of one digit sit in that order inside the
+        // tile: a key whose top bits differ from its left neighbour's opens a bucket of the direct key index here
+        // (KeyIndex, stages.cuh); the minimum over the tiles is the bucket's first position.  Saves the sweep over
+        // the sorted keys that would otherwise build the index.
+        auto index_key = [&](u32 i, u64 k, u32 g) {
+            if constexpr (PASS == PASSES - 1) {
+                if (kidx != nullptr) {
+                    const u64 b = k >> kshift;
+                    if (i == 0 || (s_keys[i - 1] >> kshift) != b) atomicMin(kidx + b, g);
+                }
+            }
+        };
         if (valid == TILE) {
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) {
                 const u32 i = tid + j * THREADS;
                 const u64 k = s_keys[i];
-                out[s_goff[digit_of<PASS>(k)] + i] = k;
+                const u32 g = s_goff[digit_of<PASS>(k)] + i;
+                out[g] = k;
+                index_key(i, k, g);
             }
         } else {
             for (u32 i = tid; i < (u32)valid; i += THREADS) {
                 const u64 k = s_keys[i];
-                out[s_goff[digit_of<PASS>(k)] + i] = k;
+                const u32 g = s_goff[digit_of<PASS>(k)] + i;
+                out[g] = k;
+                index_key(i, k, g);
             }
         }
         if (!PERSIST || next_tile >= ntiles) break;
@@ -328,7 +344,8 @@ int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, c
         if (grid > (u64)resident) grid = resident;
     }
     kern<<<(unsigned)grid, THREADS, S::bytes, st>>>(in, out, (u32)n, (u32)ntiles, ws.hist + PASS * RADIX, ws.lookback,
-                                                      ws.tile_counter + PASS, (u64)(PASS + 1) << 56);
+                                                      ws.tile_counter + PASS, (u64)(PASS + 1) << 56,
+                                                      PASS == PASSES - 1 ? ws.key_index : nullptr, 64 - ws.key_index_bits);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -388,23 +405,31 @@ int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg) {
 // Sorts `n` keys (n < 2^32 per call: one device's share).  `a` holds the input; `b` is scratch of the
 // same size.  Returns in *result which of the two buffers holds the sorted keys (passes whose digit
 // is constant are skipped).
-int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t st, u64** result) {
+int radix_sort_clear(const SortWorkspace& ws, cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(ws.hist, 0, PASSES * RADIX * 8 + 64 + ws.ntiles * RADIX * 8, st));
+    return 0;
+}
+
+int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t st, u64** result, bool hist_ready) {
     *result = a;
     if (n <= 1) return 0;
     if (n >= (1ull << 32) - (1u << 16)) {
         set_error("radix_sort_u64: at most 2^32 - 65536 keys per device call");
         return -1;
     }
-    CUDA_TRY(cudaMemsetAsync(ws.hist, 0, PASSES * RADIX * 8 + 64 + ws.ntiles * RADIX * 8, st));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    u64 want = (n / 2 + 511) / 512;
-    unsigned hgrid = (unsigned)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
-    radix_hist_kernel<512><<<hgrid, 512, 0, st>>>(a, n, ws.hist);
-    CUDA_TRY(cudaGetLastError());
+    if (!hist_ready) {
+        if (radix_sort_clear(ws, st)) return -1;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        u64 want = (n / 2 + 511) / 512;
+        unsigned hgrid = (unsigned)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
+        radix_hist_kernel<512><<<hgrid, 512, 0, st>>>(a, n, ws.hist);
+        CUDA_TRY(cudaGetLastError());
+        DEBWT_COUNT(1);
+    }
     radix_scan_kernel<<<1, RADIX, 0, st>>>(ws.hist, n, ws.skip);
-    DEBWT_COUNT(2);
+    DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     u32 skip[PASSES];
     CUDA_TRY(cudaMemcpyAsync(skip, ws.skip, sizeof skip, cudaMemcpyDeviceToHost, st));
@@ -440,6 +465,7 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
     }
     if (ws.ev_sweep_end) CUDA_TRY(cudaEventRecord(ws.ev_sweep_end, st));
     if (ws.sweeps_out) *ws.sweeps_out = sweeps;
+    if (ws.key_index_done) *ws.key_index_done = ws.key_index != nullptr && !skip[PASSES - 1];
     *result = src;
     return 0;
 }

@@ -13,11 +13,20 @@ struct SortWorkspace {
     u64 ntiles = 0;
     cudaEvent_t ev_sweep_begin = nullptr, ev_sweep_end = nullptr;   // optional: bracket the scatter passes
     int* sweeps_out = nullptr;                                        // optional: number of passes launched
+    // optional: the last pass also marks the direct key index (KeyIndex::idx, preset to 0xFFFFFFFF, `key_index_bits`
+    // top bits); *key_index_done tells whether it ran (a constant top digit skips the pass)
+    u32* key_index = nullptr;
+    int key_index_bits = 0;
+    bool* key_index_done = nullptr;
 };
 
 int sort_config_tile(int cfg);
 size_t sort_workspace_bytes(u64 n, int cfg);
 int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg);
-int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t st, u64** result);
+// hist_ready: the caller zeroed the workspace with radix_sort_clear() and filled ws.hist ([8][256] digit counts of
+// exactly these n keys, pass p = bits 8p..8p+7) itself, e.g. from the text (k_text_digit_hist); the key sweep that
+// would count them is skipped.
+int radix_sort_clear(const SortWorkspace& ws, cudaStream_t st);
+int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t st, u64** result, bool hist_ready = false);
 
 }  // namespace debwt

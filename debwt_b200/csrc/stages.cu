@@ -269,6 +269,76 @@ int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, 
     return 0;
 }
 
+// ---- digit histograms of all keys, straight from the packed text ------------------------------
+// Every key is a 32-base window of the text, so its digit of pass p (bits 8p..8p+7 = bases 28-4p..31-4p) is the
+// 4-mer that starts 28-4p bases after the window: all eight histograms are the 4-mer histogram of the text minus
+// the 4-mers too close to a record end to be that digit of any in-record window.  One sweep over n/4 bytes with one
+// shared-memory count per base replaces a sweep over 8n bytes with eight counts per key (src/mySort.c:98-103 builds
+// its bucket table from the k-mers themselves).
+namespace {
+constexpr int TH_TPB = 256;
+
+__global__ void __launch_bounds__(TH_TPB) text_hist_kernel(const u64* __restrict__ words, u64 n, u64* __restrict__ ghist) {
+    __shared__ u32 sh[TH_TPB / 32][256];
+    for (int i = threadIdx.x; i < (TH_TPB / 32) * 256; i += TH_TPB) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    u32* mine = sh[threadIdx.x >> 5];
+    const u64 nw = (n + 31) / 32;
+    for (u64 w = (u64)blockIdx.x * TH_TPB + threadIdx.x; w < nw; w += (u64)gridDim.x * TH_TPB) {
+        const u64 w0 = words[w], w1 = words[w + 1];
+        const u64 left = n - w * 32;
+        if (left >= 32) {
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const u64 x = b ? ((w0 << (2 * b)) | (w1 >> (64 - 2 * b))) : w0;
+                atomicAdd(mine + (u32)(x >> 56), 1u);
+            }
+        } else {
+            for (int b = 0; b < (int)left; ++b) {
+                const u64 x = b ? ((w0 << (2 * b)) | (w1 >> (64 - 2 * b))) : w0;
+                atomicAdd(mine + (u32)(x >> 56), 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 256; j += TH_TPB) {
+        u32 c = 0;
+#pragma unroll
+        for (int w = 0; w < TH_TPB / 32; ++w) c += sh[w][j];
+        if (c) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) atomicAdd(reinterpret_cast<unsigned long long*>(ghist + p * 256 + j), (unsigned long long)c);
+        }
+    }
+}
+
+// one thread per (record, pass): take back the 4-mers at the o = 28-4p positions after the record start and at the
+// 32-o positions up to and including the separator
+__global__ void __launch_bounds__(TH_TPB) text_hist_fix_kernel(const u64* __restrict__ words, const u64* __restrict__ seps,
+                                                              u64 n_rec, u64* __restrict__ ghist) {
+    const u64 t = (u64)blockIdx.x * TH_TPB + threadIdx.x;
+    if (t >= n_rec * 8) return;
+    const u64 r = t >> 3;
+    const u32 p = (u32)(t & 7), o = 28 - 4 * p;
+    const u64 s = r ? seps[r - 1] + 1 : 0, e = seps[r];
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(ghist + p * 256);
+    for (u64 q = s; q < s + o; ++q) atomicAdd(h + (text_window32(words, q) >> 56), ~0ull);
+    for (u64 q = e - 31 + o; q <= e; ++q) atomicAdd(h + (text_window32(words, q) >> 56), ~0ull);
+}
+}  // namespace
+
+bool text_digit_hist_applies(u64 n, u64 n_rec) { return n_rec * 2048 <= n; }
+
+int k_text_digit_hist(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* ghist, cudaStream_t st) {
+    const u64 nw = (n + 31) / 32;
+    const u64 want = (nw + TH_TPB - 1) / TH_TPB;
+    text_hist_kernel<<<(unsigned)(want < 148u * 8u ? (want ? want : 1) : 148u * 8u), TH_TPB, 0, st>>>(words, n, ghist);
+    text_hist_fix_kernel<<<grid_for(n_rec * 8, TH_TPB), TH_TPB, 0, st>>>(words, d_seps, n_rec, ghist);
+    DEBWT_COUNT(2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 namespace {
 __global__ void __launch_bounds__(TPB) diff_kernel(const u64* __restrict__ starts, u64 d, u64 n, u64* __restrict__ counts) {
     const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
@@ -497,13 +567,26 @@ __global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict_
 
 }  // namespace
 
-int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
+int k_key_index_init(KeyIndex ki, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(ki.idx, 0xFF, ((1ull << ki.bits) + 1) * 4, st));
-    if (n) key_index_mark_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, ki);
+    return 0;
+}
+
+// marked = the last sort pass already recorded every bucket's first position (SortWorkspace::key_index)
+int k_key_index_finish(const u64* sorted, u64 n, KeyIndex ki, bool marked, cudaStream_t st) {
+    if (n && !marked) {
+        key_index_mark_kernel<<<grid_for(n, TPB), TPB, 0, st>>>(sorted, n, ki);
+        DEBWT_COUNT(1);
+    }
     key_index_fill_kernel<<<grid_for((1ull << ki.bits) + 1, TPB), TPB, 0, st>>>(sorted, n, ki);
-    DEBWT_COUNT(2);
+    DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
+    if (k_key_index_init(ki, st)) return -1;
+    return k_key_index_finish(sorted, n, ki, false, st);
 }
 
 int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t st) {

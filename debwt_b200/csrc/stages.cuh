@@ -16,6 +16,11 @@ inline u64 text_words(u64 n) { return (n + 32 + 31) / 32 + 1; }
 // all in-record 32-mers; key index of window p in record r is p - 32 r.  keys: n - 32 R entries.
 int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st);
 
+// [8][256] digit counts of the keys k_extract writes, computed from the packed text (see stages.cu); applies when the
+// per-record corrections are negligible next to the sweep.
+bool text_digit_hist_applies(u64 n, u64 n_rec);
+int k_text_digit_hist(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* ghist, cudaStream_t st);
+
 // ---- K4 count-by-sort (API parity with the reference's kmerInfo records) -------------------
 // returns D through *d_total; kmers/counts sized >= n
 int k_rle(const u64* sorted, u64 n, u64* kmers, u64* counts, void* workspace, u64* d_total, cudaStream_t st);
@@ -32,6 +37,9 @@ inline int key_index_bits(u64 n) {
     return b;
 }
 int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st);
+// the same in two steps around a sort whose last pass marks the buckets (SortWorkspace::key_index)
+int k_key_index_init(KeyIndex ki, cudaStream_t st);
+int k_key_index_finish(const u64* sorted, u64 n, KeyIndex ki, bool marked, cudaStream_t st);
 __host__ __device__ __forceinline__ u64 indexed_lower_bound(const u64* __restrict__ k, const KeyIndex& ki, u64 q) {
     const u64 t = q >> (64 - ki.bits);
     return lower_bound_u64(k, ki.idx[t], ki.idx[t + 1], q);
