@@ -19,16 +19,18 @@ d_slice = torch.from_numpy(text[lo:hi].copy()).cuda()
 N = int(text.size)
 del text
 times = []
-for it in range(3):
-    stats = {}
+for it in range(4):
+    stats = {"profile": it == 3}        # last iteration: synchronised per-phase wall times (not a timing run)
     comm.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
     out = D.build_sharded(None, seps, comm, ops, stats, n_symbols=N, ascii_slice=d_slice, fetch=(it == 2))
+    if it == 2: fetched = out
+    if it == 3: prof = stats.get("phases_ms")
     torch.cuda.synchronize(); times.append((time.perf_counter() - t0) * 1e3)
 if rank == 0:
-    w, s, d = out
+    w, s, d = fetched
     res = {"n_gpus": comm.size, "n_bases": n, "gen_s": tg, "ms_per_build": times, "Mbp_s": n / min(times[:2]) / 1e3,
            "sha256": hashlib.sha256(w.tobytes()).hexdigest(), "sharp_sha256": hashlib.sha256(s.tobytes()).hexdigest(),
            "dollar": int(d[0]), "keys_local": stats["keys_local"], "n_branch": stats["n_branch"], "n_blue": stats["n_blue"],
-           "n_codes": stats["n_codes"], "sort": ops.sort_stats}
+           "n_codes": stats["n_codes"], "sort": ops.sort_stats, "rank0_phases_ms": prof}
     print(json.dumps(res), flush=True)
 dist.destroy_process_group()
