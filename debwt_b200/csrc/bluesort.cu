@@ -474,6 +474,38 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
     }
 }
 
+// One warp puts `size` <= 32 entries that agree on their first `depth` codes into their final order: every lane
+// fetches its word at `depth` once, the pairwise comparisons then run on registers and only walk the code strings when
+// two words tie as well.
+__device__ __forceinline__ void warp_rank_short(const SpView& sp, u64* ent, u32 size, u32 depth) {
+    const u32 lane = threadIdx.x & 31;
+    const bool mem = lane < size;
+    const u64 e = mem ? ent[lane] : 0;
+    u64 nw = 0;
+    u32 np = 0;
+    if (mem) {
+        const u64 sidx = (e >> 4) + depth;
+        nw = text_window32(sp.codes, sidx);
+        np = (fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
+    }
+    u32 rank = 0;
+    for (u32 j = 0; j < size; ++j) {
+        __syncwarp();
+        const u64 ej = __shfl_sync(0xffffffffu, e, j);
+        const u64 wj = __shfl_sync(0xffffffffu, nw, j);
+        const u32 pj = __shfl_sync(0xffffffffu, np, j);
+        if (mem && j != lane) {
+            bool less;
+            if (pj && np) less = wj != nw ? wj < nw : sp_less_from(sp, ej >> 4, e >> 4, depth + 32);
+            else less = sp_less_from(sp, ej >> 4, e >> 4, depth);
+            if (less) ++rank;
+        }
+    }
+    __syncwarp();
+    if (mem) ent[rank] = e;
+    __syncwarp();
+}
+
 template <int NT, int CH, int MINB>
 __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
                                                          const u32* __restrict__ n_items_ptr, WorkLists next,
@@ -485,113 +517,142 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
     s.key = s.ent + CH;
     s.tag = reinterpret_cast<u32*>(s.key + CH);
     __shared__ int s_flag, s_mixed;
+    __shared__ u32 s_cnt[4];
+    constexpr u32 MAX_PEEL = 64;           // dominant-word peels per item and launch
     for (u32 idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
         const WorkItem it = items[idx];
-        const u32 len = it.len, depth = it.depth;
+        const u32 len = it.len;
         const bool in_hbm = len > (u32)CH;
         SegArrays g;
         g.ent = blue + it.off;
         g.key = in_hbm ? g_key + it.off : s.key;
         g.tag = in_hbm ? g_tag + it.off : s.tag;
         const SegArrays& w = in_hbm ? g : s;
-        if (threadIdx.x == 0) { s_flag = 0; s_mixed = 0; }
-        __syncthreads();
-        const u32 prev0 = (u32)(g.ent[0] & 15ull);
-        // ---- stage the entries and fetch their code word at this depth ----
-        for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
-            const u64 e = g.ent[t];
-            if ((u32)(e & 15ull) != prev0) s_mixed = 1;
-            if (!in_hbm) s.ent[t] = e;
-            const u64 sidx = (e >> 4) + depth;
-            w.key[t] = text_window32(sp.codes, sidx);
-            const bool plain = fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes;
-            w.tag[t] = plain ? 1u : 0u;
-            if (!plain) s_flag = 1;
+        if (!in_hbm) {
+            for (u32 t = threadIdx.x; t < len; t += blockDim.x) s.ent[t] = g.ent[t];
         }
-        __syncthreads();
-        const bool fallback = s_flag != 0, mixed = s_mixed != 0;
-        __syncthreads();
-        if (!mixed) {
-            // every prev symbol equal: any order gives the same BWT (src/sortBlue.c:192-219)
-        } else if (fallback) {
-            LessFromDepth lf{sp, depth};
-            net_sort<CH>(g, s, len, !in_hbm, lf);           // final order for this item
-        } else {
-            net_sort<CH>(g, s, len, !in_hbm, LessKey());
-            // ---- runs of equal words: head index of every entry (max-scan over "own index if head") ----
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = (t == 0 || w.key[t] != w.key[t - 1]) ? 1u : 0u;
+        // the part of the item still being refined: entries [lo, lo + vlen) agree on their first `depth` codes
+        u32 lo = 0, vlen = len, depth = it.depth, peels = 0;
+        for (;;) {
+            if (threadIdx.x == 0) { s_flag = 0; s_mixed = 0; s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
             __syncthreads();
-            u32* k32 = reinterpret_cast<u32*>(w.key);
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) k32[2 * t] = w.tag[t] ? t : 0u;
+            SegArrays v;
+            v.ent = w.ent + lo; v.key = w.key + lo; v.tag = w.tag + lo;
+            const u64 voff = it.off + lo;
+            if (peels == MAX_PEEL) {                  // keep the launch bounded: the rest of the tie goes to the next round
+                if (threadIdx.x == 0) { WorkItem nw; nw.off = voff; nw.len = vlen; nw.depth = depth; push_item(next, nw); }
+                break;
+            }
+            // ---- fetch the code word of every entry at this depth ----
+            const u32 prev0 = (u32)(v.ent[0] & 15ull);
+            for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) {
+                const u64 e = v.ent[t];
+                if ((u32)(e & 15ull) != prev0) s_mixed = 1;
+                const u64 sidx = (e >> 4) + depth;
+                v.key[t] = text_window32(sp.codes, sidx);
+                const bool plain = fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes;
+                v.tag[t] = plain ? 1u : 0u;
+                if (!plain) s_flag = 1;
+            }
+            __syncthreads();
+            const bool fallback = s_flag != 0, mixed = s_mixed != 0;
+            if (!mixed) break;         // every prev symbol equal: any order gives the same BWT (src/sortBlue.c:192-219)
+            if (fallback) {
+                LessFromDepth lf{sp, depth};
+                SegArrays gv = g;
+                gv.ent += lo; gv.key += lo; gv.tag += lo;
+                net_sort<CH>(gv, in_hbm ? s : v, vlen, !in_hbm, lf);       // final order for this item
+                break;
+            }
+            // ---- dominant word (the copies of a repeat that agree on these 32 codes as well): three-way partition
+            //      around it instead of a sort; the equal part is refined further right here, 32 codes deeper ----
+            if (!in_hbm && vlen > 32) {
+                const u64 pivot = v.key[vlen >> 1];
+                for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) {
+                    const u64 kx = v.key[t];
+                    const u32 cls = kx < pivot ? 0u : (kx == pivot ? 1u : 2u);
+                    v.tag[t] = cls;
+                    atomicAdd(&s_cnt[cls], 1u);
+                }
+                __syncthreads();
+                const u32 n_lt = s_cnt[0], n_eq = s_cnt[1], n_gt = s_cnt[2];
+                __syncthreads();
+                if (2 * n_eq >= vlen) {
+                    if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = n_lt; s_cnt[2] = n_lt + n_eq; }
+                    __syncthreads();
+                    for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) v.key[atomicAdd(&s_cnt[v.tag[t]], 1u)] = v.ent[t];
+                    __syncthreads();
+                    for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) v.ent[t] = v.key[t];
+                    __syncthreads();
+                    // the two minorities: a warp orders a short one right away, a long one is an item of its own
+                    if (threadIdx.x == 0) {
+                        WorkItem nw;
+                        nw.depth = depth;
+                        if (n_lt > 32) { nw.off = voff; nw.len = n_lt; push_item(next, nw); }
+                        if (n_gt > 32) { nw.off = voff + n_lt + n_eq; nw.len = n_gt; push_item(next, nw); }
+                    }
+                    if ((threadIdx.x >> 5) == 0 && n_lt >= 2 && n_lt <= 32) warp_rank_short(sp, v.ent, n_lt, depth);
+                    if ((threadIdx.x >> 5) == 1 && n_gt >= 2 && n_gt <= 32) warp_rank_short(sp, v.ent + n_lt + n_eq, n_gt, depth);
+                    lo += n_lt; vlen = n_eq; depth += 32; ++peels;
+                    __syncthreads();
+                    continue;
+                }
+            }
+            {
+                SegArrays gv = g;
+                gv.ent += lo; gv.key += lo; gv.tag += lo;
+                net_sort<CH>(gv, in_hbm ? s : v, vlen, !in_hbm, LessKey());
+            }
+            // ---- runs of equal words: head index of every entry (max-scan over "own index if head") ----
+            for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) v.tag[t] = (t == 0 || v.key[t] != v.key[t - 1]) ? 1u : 0u;
+            __syncthreads();
+            u32* k32 = reinterpret_cast<u32*>(v.key);
+            for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) k32[2 * t] = v.tag[t] ? t : 0u;
             __syncthreads();
             u32 ph = 0;
-            for (u32 d = 1; d < len; d <<= 1) {
-                for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
-                    u32 v = k32[2 * t + ph];
-                    if (t >= d) { const u32 o = k32[2 * (t - d) + ph]; v = o > v ? o : v; }
-                    k32[2 * t + (ph ^ 1u)] = v;
+            for (u32 d = 1; d < vlen; d <<= 1) {
+                for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) {
+                    u32 x = k32[2 * t + ph];
+                    if (t >= d) { const u32 o = k32[2 * (t - d) + ph]; x = o > x ? o : x; }
+                    k32[2 * t + (ph ^ 1u)] = x;
                 }
                 __syncthreads();
                 ph ^= 1u;
             }
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) w.tag[t] = k32[2 * t + ph];
+            for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) v.tag[t] = k32[2 * t + ph];
             __syncthreads();
             // ---- which runs still hold two different prev symbols (flag at the run head) ----
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) k32[2 * t] = 0u;
+            for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) k32[2 * t] = 0u;
             __syncthreads();
-            for (u32 t = threadIdx.x + 1; t < len; t += blockDim.x) {
-                const u32 h = w.tag[t];
-                if (h == w.tag[t - 1] && ((w.ent[t] ^ w.ent[t - 1]) & 15ull)) k32[2 * h] = 1u;
+            for (u32 t = threadIdx.x + 1; t < vlen; t += blockDim.x) {
+                const u32 h = v.tag[t];
+                if (h == v.tag[t - 1] && ((v.ent[t] ^ v.ent[t - 1]) & 15ull)) k32[2 * h] = 1u;
             }
             __syncthreads();
             // ---- long unresolved runs go to the next round (pushed by the run's last entry) ----
-            for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
-                const u32 h = w.tag[t];
-                if ((t + 1 == len || w.tag[t + 1] != h) && k32[2 * h]) {
+            for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) {
+                const u32 h = v.tag[t];
+                if ((t + 1 == vlen || v.tag[t + 1] != h) && k32[2 * h]) {
                     const u32 size = t + 1 - h;
                     if (size > 32) {
                         WorkItem nw;
-                        nw.off = it.off + h; nw.len = size; nw.depth = depth + 32;
+                        nw.off = voff + h; nw.len = size; nw.depth = depth + 32;
                         push_item(next, nw);
                     }
                 }
             }
             // ---- short unresolved runs: one warp each, rank by counting with direct string comparisons ----
             const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwp = blockDim.x >> 5;
-            for (u32 h = wid; h < len; h += nwp) {
-                if (w.tag[h] != h || !k32[2 * h]) continue;                            // warp-uniform
-                const bool mem = h + lane < len && w.tag[h + lane] == h;
+            for (u32 h = wid; h < vlen; h += nwp) {
+                if (v.tag[h] != h || !k32[2 * h]) continue;                            // warp-uniform
+                const bool mem = h + lane < vlen && v.tag[h + lane] == h;
                 const u32 size = __popc(__ballot_sync(0xffffffffu, mem));
-                if (h + 32 < len && w.tag[h + 32] == h) continue;                      // long run: next round
-                const u64 e = mem ? w.ent[h + lane] : 0;
-                // every lane fetches its next word once; the pairwise comparisons then run on registers and only
-                // walk the code strings when two next words tie as well
-                u64 nw = 0;
-                u32 np = 0;
-                if (mem) {
-                    const u64 sidx = (e >> 4) + depth + 32;
-                    nw = text_window32(sp.codes, sidx);
-                    np = (fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
-                }
-                u32 rank = 0;
-                for (u32 j = 0; j < size; ++j) {
-                    __syncwarp();
-                    const u64 ej = __shfl_sync(0xffffffffu, e, j);
-                    const u64 wj = __shfl_sync(0xffffffffu, nw, j);
-                    const u32 pj = __shfl_sync(0xffffffffu, np, j);
-                    if (mem && j != lane) {
-                        bool less;
-                        if (pj && np) less = wj != nw ? wj < nw : sp_less_from(sp, ej >> 4, e >> 4, depth + 64);
-                        else less = sp_less_from(sp, ej >> 4, e >> 4, depth + 32);
-                        if (less) ++rank;
-                    }
-                }
-                __syncwarp();
-                if (mem) w.ent[h + rank] = e;
-                __syncwarp();
+                if (h + 32 < vlen && v.tag[h + 32] == h) continue;                     // long run: next round
+                warp_rank_short(sp, v.ent + h, size, depth + 32);
             }
-            __syncthreads();
+            break;
         }
+        __syncthreads();
         if (!in_hbm) {
             for (u32 t = threadIdx.x; t < len; t += blockDim.x) g.ent[t] = s.ent[t];
         }
