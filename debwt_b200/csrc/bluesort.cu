@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
     s.tag = reinterpret_cast<u32*>(s.key + CH);
     __shared__ int s_flag, s_mixed;
     __shared__ u32 s_cnt[4];
+    __shared__ u32 s_list[CH / 2];         // short unresolved runs of the current item: (size << 16) | head
     constexpr u32 MAX_PEEL = 64;           // dominant-word peels per item and launch
     for (u32 idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
         const WorkItem it = items[idx];
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
         // the part of the item still being refined: entries [lo, lo + vlen) agree on their first `depth` codes
         u32 lo = 0, vlen = len, depth = it.depth, peels = 0;
         for (;;) {
-            if (threadIdx.x == 0) { s_flag = 0; s_mixed = 0; s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
+            if (threadIdx.x == 0) { s_flag = 0; s_mixed = 0; s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
             __syncthreads();
             SegArrays v;
             v.ent = w.ent + lo; v.key = w.key + lo; v.tag = w.tag + lo;
@@ -629,7 +630,8 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
                 if (h == v.tag[t - 1] && ((v.ent[t] ^ v.ent[t - 1]) & 15ull)) k32[2 * h] = 1u;
             }
             __syncthreads();
-            // ---- long unresolved runs go to the next round (pushed by the run's last entry) ----
+            // ---- unresolved runs, reported by their last entry: long ones go to the next round, short ones are
+            //      listed and ordered right away, one warp each, by direct comparisons ----
             for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) {
                 const u32 h = v.tag[t];
                 if ((t + 1 == vlen || v.tag[t + 1] != h) && k32[2 * h]) {
@@ -638,17 +640,16 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
                         WorkItem nw;
                         nw.off = voff + h; nw.len = size; nw.depth = depth + 32;
                         push_item(next, nw);
+                    } else {
+                        s_list[atomicAdd(&s_cnt[3], 1u)] = (size << 16) | h;
                     }
                 }
             }
-            // ---- short unresolved runs: one warp each, rank by counting with direct string comparisons ----
-            const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwp = blockDim.x >> 5;
-            for (u32 h = wid; h < vlen; h += nwp) {
-                if (v.tag[h] != h || !k32[2 * h]) continue;                            // warp-uniform
-                const bool mem = h + lane < vlen && v.tag[h + lane] == h;
-                const u32 size = __popc(__ballot_sync(0xffffffffu, mem));
-                if (h + 32 < vlen && v.tag[h + 32] == h) continue;                     // long run: next round
-                warp_rank_short(sp, v.ent + h, size, depth + 32);
+            __syncthreads();
+            const u32 n_list = s_cnt[3];
+            for (u32 q = threadIdx.x >> 5; q < n_list; q += blockDim.x >> 5) {
+                const u32 x = s_list[q];
+                warp_rank_short(sp, v.ent + (x & 0xffffu), x >> 16, depth + 32);
             }
             break;
         }
