@@ -7,6 +7,8 @@
 // range-aware variants of the single-GPU stages plus the bucket-by-owner partition.
 #include "dist_kernels.cuh"
 
+#include <cstdlib>
+
 #include "stages_dev.cuh"
 
 namespace debwt {
@@ -198,6 +200,72 @@ __global__ void __launch_bounds__(TPB) partition_scatter_p2p_kernel(const u64* _
         const u32 start = __shfl_sync(0xffffffffu, run, d < n_ranks ? d : 0);
         if (d < n_ranks) dst.ptr[d][s_base[d] + start + rank] = a[i];
         run += add;
+    }
+}
+
+// Same exchange with the block's tile first reordered by destination in shared memory: consecutive threads then store
+// consecutive items of one destination's run, so every peer store of a warp is one contiguous 256-byte run instead of
+// G short ones (a 32-64 byte store per destination and warp row reached only a fifth of the NVLink bandwidth on the
+// 3.1 Gbp build; profiles/r01_c3_3p1gbp_8gpu.log).
+__global__ void __launch_bounds__(TPB) partition_scatter_p2p_staged_kernel(const u64* __restrict__ a, OwnerFn owner, u64 n,
+                                                                          u32 n_ranks, u64* __restrict__ cursors, PeerDst dst) {
+    constexpr int NW = TPB / 32;
+    __shared__ u32 s_wcnt[NW][MAX_RANKS];
+    __shared__ u64 s_base[MAX_RANKS];
+    __shared__ u32 s_off[MAX_RANKS + 1];
+    __shared__ u64 s_items[PART_TILE];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+    const u64 base = (u64)blockIdx.x * PART_TILE;
+    u8 dd[PART_ITEMS];
+    u64 vv[PART_ITEMS];
+    u32 mine = 0;
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        const u64 i = base + (u64)j * TPB + threadIdx.x;
+        const u32 d = i < n ? owner(a, i) : 255u;
+        vv[j] = i < n ? a[i] : 0;
+        dd[j] = (u8)d;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 bal = __ballot_sync(0xffffffffu, d == g);
+            if (lane == g) mine += __popc(bal);
+        }
+    }
+    if (lane < MAX_RANKS) s_wcnt[warp][lane] = lane < n_ranks ? mine : 0;
+    __syncthreads();
+    if (threadIdx.x < n_ranks) {
+        u32 run = 0;
+        for (int w = 0; w < NW; ++w) { const u32 c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
+        s_base[threadIdx.x] = run ? atomicAdd(&cursors[threadIdx.x], (u64)run) : 0;
+        s_off[threadIdx.x + 1] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        s_off[0] = 0;
+        for (u32 g = 0; g < n_ranks; ++g) { const u32 c = s_off[g + 1]; s_off[g + 1] = run + c; run += c; }
+    }
+    __syncthreads();
+    u32 run = lane < n_ranks ? s_wcnt[warp][lane] : 0;
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+        const u32 d = dd[j];
+        u32 rank = 0, add = 0;
+        for (u32 g = 0; g < n_ranks; ++g) {
+            const u32 bal = __ballot_sync(0xffffffffu, d == g);
+            if (d == g) rank = __popc(bal & lt);
+            if (lane == g) add = __popc(bal);
+        }
+        const u32 start = __shfl_sync(0xffffffffu, run, d < n_ranks ? d : 0);
+        if (d < n_ranks) s_items[s_off[d] + start + rank] = vv[j];
+        run += add;
+    }
+    __syncthreads();
+    const u32 total = s_off[n_ranks];
+    for (u32 p = threadIdx.x; p < total; p += TPB) {
+        u32 d = 0;
+        while (s_off[d + 1] <= p) ++d;
+        dst.ptr[d][s_base[d] + (p - s_off[d])] = s_items[p];
     }
 }
 
@@ -461,7 +529,9 @@ int k_partition_scatter_p2p(const u64* a, const PartitionBy& by, u64 n, u32 n_ra
     if (n == 0) return 0;
     PeerDst pd;
     for (u32 r = 0; r < MAX_RANKS; ++r) pd.ptr[r] = r < n_ranks ? dst[r] : nullptr;
-    partition_scatter_p2p_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd);
+    static const bool direct = getenv("DEBWT_P2P_DIRECT") != nullptr;      // the unstaged variant, kept for comparison
+    if (direct) partition_scatter_p2p_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd);
+    else partition_scatter_p2p_staged_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd);
     LAUNCHED(1);
 }
 
