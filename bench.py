@@ -296,6 +296,8 @@ def ours(args, rank, world, local_rank):
                                         "ms": sort_ms / args.steps}},
             "phases_ms": {k: last[k] for k in last if k.startswith("ms_")},
             "sizes": {k: last[k] for k in ("n_symbols", "n_keys", "n_branch", "n_blue", "n_codes", "n_special")},
+            # checksum of the packed BWT the last end-to-end step copied back: the same at every N (outside the timed regions)
+            "bwt_sha256": __import__("hashlib").sha256(h_out.numpy().tobytes()).hexdigest(),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -414,6 +416,8 @@ def ours_sharded(args, rank, world, local_rank):
                          "traffic": (traffic or {}).get("dram_bytes_per_key", None) and traffic["dram_bytes_per_key"] * nk_loc,
                          "sort_phase": {"achieved": phase, "frac": phase / peak, "bytes_per_key": 136, "ms": sort_ms / args.steps}},
             "sizes": {k: stats.get(k) for k in ("n_symbols", "n_keys", "n_branch", "n_blue", "n_codes")},
+            # checksum of the packed BWT the last end-to-end step copied back: the same at every N (outside the timed regions)
+            "bwt_sha256": __import__("hashlib").sha256(h_out.numpy().tobytes()).hexdigest(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
