@@ -685,10 +685,12 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
         // round-based refinement of the segments beyond one warp's shared-memory slice
         auto refine_small = refine_kernel<BIG_TPB, CHUNK, 2>;
         auto refine_tiny = refine_kernel<TINY_TPB, TINY, 8>;    // 8, 10 or 12 blocks per SM measured the same
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[64] = {};        // per device: function attributes belong to the device's context
+        int cur_dev = 0;
+        cudaGetDevice(&cur_dev);
+        if (!attr_done[cur_dev & 63]) {
             CUDA_TRY(cudaFuncSetAttribute(refine_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChunkSmem));
-            attr_done = true;
+            attr_done[cur_dev & 63] = true;
         }
         const u64 cap_tiny64 = bt.n_blue / 16 + n_big + 16, cap_huge64 = bt.n_blue / CHUNK + h[3] + 16;
         const u64 cap_small64 = bt.n_blue / TINY + cap_huge64 + 16;
@@ -726,6 +728,9 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
             const u32* c = cur.cnt == d_cnt ? n_fin : n_fin + 4;
             const u32* n = cur.cnt == d_cnt ? n_fin + 4 : n_fin;
             if (c[0] > cap_small || c[2] > cap_tiny || n[0] > cap_small || n[1] > cap_huge || n[2] > cap_tiny) {
+                cudaFreeAsync(lists, st);
+                cudaFreeAsync(d_cnt, st);
+                if (g_key) cudaFreeAsync(g_key, st);
                 set_error("internal: K10 work list overflow");
                 return -1;
             }

@@ -325,10 +325,12 @@ template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST>
 int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, cudaStream_t st) {
     using S = SweepSmem<THREADS, ITEMS>;
     auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS, PERSIST>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};            // per device: function attributes belong to the device's context
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (!attr_done[cur_dev & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
-        attr_done = true;
+        attr_done[cur_dev & 63] = true;
     }
     const u64 ntiles = (n + S::TILE - 1) / S::TILE;
     u64 grid = ntiles;

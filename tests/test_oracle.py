@@ -91,6 +91,18 @@ def test_c_stage_helpers_match_numpy():
     assert (km == km2).all() and (ct == ct2).all() and int(ct.sum()) == keys.size
 
 
+@pytest.mark.parametrize("name", ["c4_like_5x100k", "c3_like_600k_3rec"])
+def test_digit_histograms_from_text_equal_key_histograms(name):
+    # the identity the CUDA path uses to skip the histogram sweep over the keys (text_hist_kernel)
+    recs = as_bytes_records(seeded_records(name))
+    recs = recs + [recs[0][:33], recs[0][:40]]             # shortest legal records: the two corrections nearly touch
+    sym, seps = st.text_from_records(recs)
+    want = st.digit_histograms(st.extract_keys(sym, seps))
+    got = st.digit_histograms_from_text(sym, seps)
+    assert (want == got).all()
+    assert int(got[0].sum()) == sym.size - 32 * len(recs)
+
+
 def test_lf_inversion_roundtrip():
     recs = as_bytes_records(seeded_records("c3_like_600k_3rec"))
     sym, _ = st.text_from_records(recs)
