@@ -180,7 +180,7 @@ def reference_arm(args, rank, world):
     t = sum(times) / len(times)
     v = nb / t / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": desc, "sample": f"first {nb} bases of the workload per step"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
