@@ -289,6 +289,7 @@ def ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (radix-sort scatter pass, %d launches/step)" % (sweeps // args.steps),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000": achieved / 8000.0,     # north_star quotes ~8 TB/s per GPU
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": 16 * nk,
                          "mean_launch_ms": per_launch_ms,
                          "traffic": (traffic or {}).get("dram_bytes_per_key", None) and traffic["dram_bytes_per_key"] * nk,
@@ -411,7 +412,8 @@ def ours_sharded(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (radix-sort scatter pass on rank 0's key range, %d launches/step)"
                                                    % (sweeps // max(args.steps, 1)),
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 16 * nk_loc, "mean_launch_ms": per_launch_ms,
                          "traffic": (traffic or {}).get("dram_bytes_per_key", None) and traffic["dram_bytes_per_key"] * nk_loc,
                          "sort_phase": {"achieved": phase, "frac": phase / peak, "bytes_per_key": 136, "ms": sort_ms / args.steps}},
