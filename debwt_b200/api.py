@@ -184,3 +184,10 @@ def bench_sort(n: int, device: int = 0, cfg: int = 0, iters: int = 5) -> float:
     ms = ctypes.c_float()
     check(lib().debwt_bench_sort(device, n, cfg, iters, ctypes.byref(ms)))
     return ms.value
+
+
+def bench_sort_passes(n: int, device: int = 0, cfg: int = 0, iters: int = 5):
+    """(mean ms per whole sort, mean ms per digit pass) on `n` device-generated pseudo-random keys"""
+    ms, msp = ctypes.c_float(), ctypes.c_float()
+    check(lib().debwt_bench_sort_passes(device, n, cfg, iters, ctypes.byref(ms), ctypes.byref(msp)))
+    return ms.value, msp.value

@@ -26,7 +26,8 @@ class Stats(ctypes.Structure):
     _fields_ = [(n, c_u64) for n in ("n_symbols", "n_records", "n_keys", "n_branch", "n_blue", "n_codes", "n_special")] + \
                [(n, ctypes.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_sort_sweeps", "ms_classify", "ms_special",
                                               "ms_codes", "ms_bluesort", "ms_emit", "ms_d2h", "ms_total")] + \
-               [("sort_launches", ctypes.c_uint32), ("sort_sweeps", ctypes.c_uint32), ("total_launches", ctypes.c_uint32)]
+               [("sort_launches", ctypes.c_uint32), ("sort_sweeps", ctypes.c_uint32), ("total_launches", ctypes.c_uint32),
+                ("reserved_", ctypes.c_uint32), ("arena_bytes", c_u64), ("arena_used_bytes", c_u64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -52,6 +53,8 @@ _SIGS = {
     "debwt_k_rle": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_p, c_p, ctypes.POINTER(c_u64)]),
     "debwt_k_group_masks": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_p, c_u64, c_p]),
     "debwt_bench_sort": (ctypes.c_int, [ctypes.c_int, c_u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+    "debwt_bench_sort_passes": (ctypes.c_int, [ctypes.c_int, c_u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                                ctypes.POINTER(ctypes.c_float)]),
 }
 
 _lib = None

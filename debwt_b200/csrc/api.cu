@@ -39,9 +39,9 @@ void set_error(const std::string& msg) { g_err = msg; }
 // multi-hundred-MB buffers of a build; an arena makes steady-state builds allocation-free.
 // ---------------------------------------------------------------------------------------------
 struct DevPool {
-    struct Chunk { char* base; size_t cap, used; };
+    struct Chunk { char* base; size_t cap, used; bool owned; };
     cudaStream_t st = nullptr;
-    std::vector<Chunk> chunks;
+    std::vector<Chunk> chunks;          // adopted (borrowed) regions first, then the chunks this pool cudaMalloc'ed
     size_t next_chunk = 256ull << 20;
     void hint(size_t bytes) { if (bytes > next_chunk) next_chunk = bytes; }
     int alloc(void** p, size_t bytes) {
@@ -50,26 +50,53 @@ struct DevPool {
         for (auto& c : chunks) {
             if (c.cap - c.used >= bytes) { *p = c.base + c.used; c.used += bytes; return 0; }
         }
-        Chunk c{nullptr, bytes > next_chunk ? bytes : next_chunk, 0};
+        Chunk c{nullptr, bytes > next_chunk ? bytes : next_chunk, 0, true};
         CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.base), c.cap));
         *p = c.base;
         c.used = bytes;
         chunks.push_back(c);
         return 0;
     }
-    // only the most recent allocation of a chunk can be handed back (stack discipline); anything else
-    // stays reserved until the next reset
-    void release(void* p) {
-        if (!p) return;
-        for (auto& c : chunks) {
-            char* q = static_cast<char*>(p);
-            if (q >= c.base && q < c.base + c.used) { last_release_hint(c, q); return; }
-        }
+    // A buffer of this pool that the build no longer needs (the ping-pong half the sort did not end in, the ASCII text
+    // after packing) becomes a region later allocations are served from first.  It stays reserved in its own chunk,
+    // so nothing is handed out twice; adopted regions vanish at the next rewind.
+    void adopt(void* p, size_t bytes) {
+        char* q = static_cast<char*>(p);
+        char* a = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(q) + 511) & ~(uintptr_t)511);
+        if (!p || a >= q + bytes) return;
+        const size_t cap = (size_t)(q + bytes - a) & ~(size_t)511;
+        if (cap) chunks.insert(chunks.begin(), Chunk{a, cap, 0, false});
     }
-    void last_release_hint(Chunk&, char*) {}
-    void release_all() { for (auto& c : chunks) c.used = 0; }
+    // state of the owned chunks (bytes in use), to come back to before a build
+    std::vector<size_t> mark() const {
+        std::vector<size_t> m;
+        for (auto& c : chunks) if (c.owned) m.push_back(c.used);
+        return m;
+    }
+    void rewind(const std::vector<size_t>& m) {
+        std::vector<Chunk> keep;
+        size_t i = 0;
+        for (auto& c : chunks) {
+            if (!c.owned) continue;
+            c.used = i < m.size() ? m[i] : 0;
+            ++i;
+            keep.push_back(c);
+        }
+        chunks.swap(keep);
+    }
+    void release_all() { rewind({}); }
+    size_t reserved_bytes() const {             // HBM this pool holds
+        size_t t = 0;
+        for (auto& c : chunks) if (c.owned) t += c.cap;
+        return t;
+    }
+    size_t used_bytes() const {                 // high-water marks of the owned chunks (adopted regions live inside them)
+        size_t t = 0;
+        for (auto& c : chunks) if (c.owned) t += c.used;
+        return t;
+    }
     void destroy() {
-        for (auto& c : chunks) cudaFree(c.base);
+        for (auto& c : chunks) if (c.owned) cudaFree(c.base);
         chunks.clear();
     }
 };
@@ -88,6 +115,7 @@ struct Special {
 };
 
 constexpr u64 kMaxDeviceSpecials = 16384;   // 32 R above this: host sort (all-pairs ranking is quadratic)
+constexpr int kDefaultSortCfg = 8;          // 384 threads x 16 keys per tile, 3 CTAs/SM
 
 
 // Host part of the sentinel-window handling: from the per-suffix scan results (rank, windows, insertion
@@ -145,7 +173,7 @@ using namespace debwt;
 
 struct debwt_ctx {
     int device = 0;
-    int sort_cfg = 8;   // 384 threads x 16 keys per tile, 3 CTAs/SM (fastest measured on B200, profiles/)
+    int sort_cfg = kDefaultSortCfg;
     cudaStream_t st = nullptr;
     DevPool pool;
     // input
@@ -160,6 +188,7 @@ struct debwt_ctx {
     u64* d_dollar = nullptr;
     u64 n_words = 0;
     bool built = false;
+    std::vector<size_t> input_mark;   // pool state right after the input was set: every build starts from here
     debwt_stats stats{};
     cudaEvent_t ev[16]{};
 };
@@ -211,6 +240,7 @@ int check_seps(const T* seps, u64 n_rec, u64 n) {
 
 void reset_input(debwt_ctx* c) {
     c->pool.release_all();
+    c->input_mark.clear();
     c->d_ascii = nullptr;
     c->d_ascii_ext = nullptr;
     c->d_bwt = nullptr;
@@ -264,7 +294,7 @@ void debwt_destroy(debwt_ctx* c) {
 
 int debwt_set_sort_config(debwt_ctx* c, int cfg) {
     int old = c->sort_cfg;
-    c->sort_cfg = cfg;
+    c->sort_cfg = cfg > 0 ? cfg : kDefaultSortCfg;          // 0 = default
     return old;
 }
 
@@ -283,7 +313,7 @@ int debwt_set_records(debwt_ctx* c, const char* const* seqs, const uint64_t* len
     }
     if (check_seps(c->seps.data(), n_records, n)) return -1;
     c->n = n; c->n_rec = n_records;
-    c->pool.hint(n * 28 + (64ull << 20));
+    c->pool.hint(n * 19 + (320ull << 20));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
     if (dalloc(c->pool, &c->d_ascii, n + 64)) return -1;
     u64 off = 0;
@@ -296,10 +326,10 @@ int debwt_set_records(debwt_ctx* c, const char* const* seqs, const uint64_t* len
     CUDA_TRY(cudaMemcpyAsync(d_seps, c->seps.data(), n_records * 8, cudaMemcpyHostToDevice, c->st));
     write_seps_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, c->st>>>(c->d_ascii, d_seps, n_records);
     CUDA_TRY(cudaGetLastError());
-    c->pool.release(d_seps);
     CUDA_TRY(cudaEventRecord(c->ev[1], c->st));
     CUDA_TRY(cudaStreamSynchronize(c->st));
     CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev[0], c->ev[1]));
+    c->input_mark = c->pool.mark();
     return 0;
 }
 
@@ -310,13 +340,14 @@ int debwt_set_text(debwt_ctx* c, const char* text, uint64_t n, const uint64_t* s
     if (check_seps(seps, n_records, n)) return -1;
     c->seps.assign(seps, seps + n_records);
     c->n = n; c->n_rec = n_records;
-    c->pool.hint(n * 28 + (64ull << 20));
+    c->pool.hint(n * 19 + (320ull << 20));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
     if (dalloc(c->pool, &c->d_ascii, n + 64)) return -1;
     CUDA_TRY(cudaMemcpyAsync(c->d_ascii, text, n, cudaMemcpyHostToDevice, c->st));
     CUDA_TRY(cudaEventRecord(c->ev[1], c->st));
     CUDA_TRY(cudaStreamSynchronize(c->st));
     CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev[0], c->ev[1]));
+    c->input_mark = c->pool.mark();
     return 0;
 }
 
@@ -328,8 +359,9 @@ int debwt_set_text_device(debwt_ctx* c, const void* d_text, uint64_t n, const ui
     if (reinterpret_cast<uintptr_t>(d_text) & 15) FAIL("device text must be 16-byte aligned");
     c->seps.assign(seps, seps + n_records);
     c->n = n; c->n_rec = n_records;
-    c->pool.hint(n * 27 + (64ull << 20));
+    c->pool.hint(n * 18 + (320ull << 20));
     c->d_ascii_ext = reinterpret_cast<const u8*>(d_text);
+    c->input_mark = c->pool.mark();
     return 0;
 }
 
@@ -342,6 +374,8 @@ int debwt_build(debwt_ctx* c, int k) {
     if (!ascii) FAIL("input was consumed by a previous build; set it again");
     cudaStream_t st = c->st;
     DevPool& pool = c->pool;
+    pool.rewind(c->input_mark);          // a repeated build on the same (device-resident) input reuses the arena
+    c->built = false;
     const u64 n = c->n, R = c->n_rec, nk = n - 32 * R;
     debwt_stats& S = c->stats;
     const float keep_h2d = S.ms_h2d;
@@ -359,7 +393,7 @@ int debwt_build(debwt_ctx* c, int k) {
     CUDA_TRY(cudaMemcpyAsync(d_seps, c->seps.data(), R * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
     if (k_pack(ascii, n, d_text, d_err, st)) return -1;
-    if (c->d_ascii) { pool.release(c->d_ascii); c->d_ascii = nullptr; }
+    if (c->d_ascii) { pool.adopt(c->d_ascii, n + 64); c->d_ascii = nullptr; }
     mark();                                                                     // ev1
 
     // ---- K2 extract ----
@@ -387,8 +421,8 @@ int debwt_build(debwt_ctx* c, int k) {
     if (radix_sort_u64(d_ka, d_kb, nk, ws, st, &d_keys, text_hist)) return -1;
     S.sort_launches = g_launches - launches_before_sort;
     S.sort_sweeps = (u32)sweeps;
-    pool.release(d_sortws);
-    pool.release(d_keys == d_ka ? d_kb : d_ka);
+    pool.adopt(d_keys == d_ka ? d_kb : d_ka, (nk + 2) * 8);       // the ping-pong half the sort did not end in
+    pool.adopt(d_sortws, sort_workspace_bytes(nk, c->sort_cfg));
     u32 h_err[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(h_err, d_err, 8, cudaMemcpyDeviceToHost, st));
     mark();                                                                     // ev3
@@ -427,7 +461,6 @@ int debwt_build(debwt_ctx* c, int k) {
         CUDA_TRY(cudaMemcpyAsync(bt.blue + bt.n_branch, &m32, 4, cudaMemcpyHostToDevice, st));
     }
     if (k_branch_index(bt, st)) return -1;
-    pool.release(d_brws);
     mark();                                                                     // ev4
 
     // ---- sentinel-window suffixes: ranked on the device (32 R suffixes, all pairs), tables built on the host ----
@@ -442,7 +475,6 @@ int debwt_build(debwt_ctx* c, int k) {
         if (k_special_scan(d_text, d_seps, R, d_keys, nk, ki, d_info, st)) return -1;
         CUDA_TRY(cudaMemcpyAsync(info.data(), d_info, nspec * sizeof(SpecialInfo), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        pool.release(d_info);
     } else {
         // many records: sort on the host over a copy of the packed text (reference: qsort, src/collect#$.c:157)
         std::vector<u64> h_text(text_words(n));
@@ -472,7 +504,6 @@ int debwt_build(debwt_ctx* c, int k) {
         if (k_special_insertion(d_keys, nk, ki, d_pads, nspec, d_ins, st)) return -1;
         CUDA_TRY(cudaMemcpyAsync(h_ins.data(), d_ins, nspec * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        pool.release(d_pads);
         for (u64 t = 0; t < nspec; ++t) info[t].ins = (t & 31) ? h_ins[t] : nk;
     }
     std::vector<u64> h_rows, h_emit_pos, h_tail_pos;
@@ -540,18 +571,13 @@ int debwt_build(debwt_ctx* c, int k) {
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
 
-    // free everything except the result
-    for (void* p : {(void*)d_seps, (void*)d_text, (void*)d_err, (void*)d_keys, (void*)d_gmask, (void*)d_tot,
-                    (void*)bt.kmer, (void*)bt.head, (void*)bt.blue, (void*)bt.cursor, (void*)bt.bidx, (void*)d_pads,
-                    (void*)d_ins, (void*)d_rows, (void*)d_chr, (void*)d_emit, (void*)d_tail, (void*)d_tail_idx,
-                    (void*)d_mo, (void*)d_wp, (void*)d_blue, d_scanws, (void*)d_codes, (void*)d_sep, (void*)d_work, (void*)ki.idx})
-        pool.release(p);
-
     float* ms[] = {&S.ms_pack, &S.ms_extract, &S.ms_sort, &S.ms_classify, &S.ms_special, &S.ms_codes, &S.ms_bluesort, &S.ms_emit};
     for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventElapsedTime(ms[i], c->ev[i], c->ev[i + 1]));
     CUDA_TRY(cudaEventElapsedTime(&S.ms_total, c->ev[0], c->ev[8]));
     if (S.sort_sweeps) CUDA_TRY(cudaEventElapsedTime(&S.ms_sort_sweeps, c->ev[11], c->ev[12]));
     S.total_launches = g_launches;
+    S.arena_bytes = pool.reserved_bytes();
+    S.arena_used_bytes = pool.used_bytes();
     c->built = true;
     return 0;
 }
@@ -748,18 +774,22 @@ int debwt_special_tables(const void* info_host, const uint64_t* ins_by_t, const 
     return 0;
 }
 
-int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out) {
+int debwt_bench_sort_passes(int device, uint64_t n, int cfg, int iters, float* ms_out, float* ms_per_pass_out) {
     Scratch s;
     if (open_scratch(s, device)) return -1;
+    if (cfg == 0) cfg = kDefaultSortCfg;
     u64 *d_a, *d_b; void* d_ws;
     if (s.get(&d_a, n + 2) || s.get(&d_b, n + 2)) return -1;
     CUDA_TRY(cudaMalloc(&d_ws, sort_workspace_bytes(n, cfg)));
     s.ptrs.push_back(d_ws);
     SortWorkspace ws;
     sort_workspace_bind(ws, d_ws, n, cfg);
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0, e1, e2, e3;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-    float total = 0;
+    CUDA_TRY(cudaEventCreate(&e2)); CUDA_TRY(cudaEventCreate(&e3));
+    int sweeps = 0;
+    ws.ev_sweep_begin = e2; ws.ev_sweep_end = e3; ws.sweeps_out = &sweeps;
+    float total = 0, total_pass = 0;
     for (int it = 0; it < iters + 1; ++it) {
         splitmix_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(d_a, n, 1234 + it);
         CUDA_TRY(cudaEventRecord(e0, s.st));
@@ -767,13 +797,19 @@ int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out) 
         if (radix_sort_u64(d_a, d_b, n, ws, s.st, &res)) return -1;
         CUDA_TRY(cudaEventRecord(e1, s.st));
         CUDA_TRY(cudaStreamSynchronize(s.st));
-        float ms = 0;
+        float ms = 0, msp = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        if (it) total += ms;                         // first run is warm-up
+        if (sweeps) CUDA_TRY(cudaEventElapsedTime(&msp, e2, e3));
+        if (it) { total += ms; total_pass += sweeps ? msp / sweeps : 0.f; }      // first run is warm-up
     }
     if (ms_out) *ms_out = total / (iters > 0 ? iters : 1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_per_pass_out) *ms_per_pass_out = total_pass / (iters > 0 ? iters : 1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return 0;
+}
+
+int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out) {
+    return debwt_bench_sort_passes(device, n, cfg, iters, ms_out, nullptr);
 }
 
 }  // extern "C"

@@ -17,18 +17,13 @@
 //   instruction-issue bound unless the per-key instruction count is kept near 2: the digit position
 //   is a template parameter, the ballot sequence is hand-written, destinations are 32-bit indices.
 //   Algorithmic traffic: 8 + 8*16 = 136 B/key.
-#include "radix_sort.cuh"
+#include "radix_common.cuh"
 
 namespace debwt {
 
 namespace {
 
-constexpr int RADIX = 256;
-constexpr int PASSES = 8;
-constexpr u64 LB_VALUE_MASK = (1ull << 56) - 1;
-constexpr u64 LB_EPOCH_MASK = 63ull << 56;
-constexpr u64 LB_AGG = 1ull << 62;
-constexpr u64 LB_INCL = 2ull << 62;
+using namespace radix;
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) radix_hist_kernel(const u64* __restrict__ keys, u64 n,
@@ -100,38 +95,10 @@ struct SweepSmem {
                                     (size_t)(THREADS / RADIX) * RADIX * 4;
 };
 
-template <int PASS>
-__device__ __forceinline__ u32 digit_of(u64 key) {
-    const u32 w = PASS < 4 ? (u32)key : (u32)(key >> 32);
-    constexpr int s = 8 * (PASS & 3);
-    return s == 24 ? (w >> 24) : ((w >> s) & 255u);
-}
-
-// lanes of the warp that hold the same 8-bit digit: one ballot per digit bit
-__device__ __forceinline__ u32 match_digit(u32 d) {
-    u32 peers;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 v, t;\n\t"
-        "and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; mov.b32 %0, v;\n\t"
-        "and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n\t"
-        "}"
-        : "=&r"(peers)
-        : "r"(d));
-    return peers;
-}
-
 // PERSIST = false: one CTA per tile.  PERSIST = true: a resident CTA loops over tiles and issues the loads
 // of its next tile right after the current one has been reordered into shared memory, so the load latency
 // and the look-back wait of tile t overlap the global loads of tile t+1 (the key registers are free then).
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST, int LB, int SLEEP, bool PRE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 ntiles, const u64* __restrict__ gbase,
                 u64* __restrict__ lookback, u32* __restrict__ tile_counter, u64 epoch, u32* __restrict__ kidx, int kshift) {
@@ -238,7 +205,9 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 nt
         }
         __syncthreads();
 
-        // ---- reorder through shared memory ----
+        // ---- reorder through shared memory (PRE: the first look-back round trip is in flight meanwhile) ----
+        u64 pre[LB];
+        if (PRE && tid < RADIX && tile != 0) lookback_fetch<LB>(lb - RADIX, tile, pre);
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const u32 d = digit_of<PASS>(key[j]);
@@ -253,32 +222,7 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 nt
         if (tid < RADIX) {
             u64 excl = 0;
             if (tile != 0) {
-                // walk the predecessors LB_BATCH at a time: the loads of one batch are independent, so a long
-                // run of count-only predecessors costs one memory round trip per batch instead of per tile
-                constexpr int LB_BATCH = 4;
-                u32 left = tile;                       // predecessors not yet consumed
-                const u64* p = lb - RADIX;             // nearest unconsumed predecessor
-                u32 spins = 0;
-                bool done = false;
-                while (!done) {
-                    u64 v[LB_BATCH];
-#pragma unroll
-                    for (int i = 0; i < LB_BATCH; ++i) v[i] = ((u32)i < left) ? ld_volatile(p - (size_t)i * RADIX) : 0;
-                    int used = 0;
-#pragma unroll
-                    for (int i = 0; i < LB_BATCH; ++i) {
-                        if (done || used != i) continue;                       // stop at the first unpublished entry
-                        if ((u32)i >= left) continue;
-                        const u64 x = v[i];
-                        if ((x & LB_EPOCH_MASK) != epoch || (x >> 62) == 0) continue;
-                        excl += x & LB_VALUE_MASK;
-                        used = i + 1;
-                        if ((x >> 62) == 2) done = true;
-                    }
-                    p -= (size_t)used * RADIX;
-                    left -= used;
-                    if (used == 0 && ++spins > (1u << 24)) __trap();           // never hang the device on a bug
-                }
+                excl = lookback_exclusive<LB, SLEEP, PRE>(lb, tile, epoch, pre);
                 st_volatile(lb, LB_INCL | epoch | (excl + vcount));
             }
             s_goff[tid] = (u32)(gbase[tid] + excl) - s_binoff[tid];
@@ -321,10 +265,10 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 nt
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST, int LB, int SLEEP, bool PRE>
 int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, cudaStream_t st) {
     using S = SweepSmem<THREADS, ITEMS>;
-    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS, PERSIST>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS, PERSIST, LB, SLEEP, PRE>;
     static bool attr_done[64] = {};            // per device: function attributes belong to the device's context
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -352,24 +296,27 @@ int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, c
     return 0;
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PERSIST = false>
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PERSIST = false, int LB = 4, int SLEEP = 0, bool PRE = false>
 int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
     switch (pass) {
-        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0, PERSIST>(in, out, n, ws, st);
-        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1, PERSIST>(in, out, n, ws, st);
-        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2, PERSIST>(in, out, n, ws, st);
-        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3, PERSIST>(in, out, n, ws, st);
-        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4, PERSIST>(in, out, n, ws, st);
-        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5, PERSIST>(in, out, n, ws, st);
-        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6, PERSIST>(in, out, n, ws, st);
-        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7, PERSIST>(in, out, n, ws, st);
+        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
     }
 }
 
 }  // namespace
 
 int sort_config_tile(int cfg) {
+    if (cfg >= TMA_CFG_BASE) return tma_config_tile(cfg);
     switch (cfg) {
+
         case 1: return 512 * 16;
         case 2: return 256 * 24;
         case 3: return 384 * 16;
@@ -390,7 +337,7 @@ int sort_config_tile(int cfg) {
 size_t sort_workspace_bytes(u64 n, int cfg) {
     const u64 tile = (u64)sort_config_tile(cfg);
     const u64 ntiles = (n + tile - 1) / tile + 1;
-    return PASSES * RADIX * 8 + 64 + ntiles * RADIX * 8;
+    return PASSES * RADIX * 8 + 64 + ntiles * RADIX * 8 + ntiles * 64;
 }
 
 int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg) {
@@ -401,6 +348,7 @@ int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg) {
     ws.lookback = ws.hist + PASSES * RADIX + 8;
     const u64 tile = (u64)sort_config_tile(cfg);
     ws.ntiles = (n + tile - 1) / tile;
+    ws.lookback_par = ws.lookback + (ws.ntiles + 1) * RADIX;
     return 0;
 }
 
@@ -408,7 +356,7 @@ int sort_workspace_bind(SortWorkspace& ws, void* mem, u64 n, int cfg) {
 // same size.  Returns in *result which of the two buffers holds the sorted keys (passes whose digit
 // is constant are skipped).
 int radix_sort_clear(const SortWorkspace& ws, cudaStream_t st) {
-    CUDA_TRY(cudaMemsetAsync(ws.hist, 0, PASSES * RADIX * 8 + 64 + ws.ntiles * RADIX * 8, st));
+    CUDA_TRY(cudaMemsetAsync(ws.hist, 0, PASSES * RADIX * 8 + 64 + (ws.ntiles + 1) * RADIX * 8 + (ws.ntiles + 1) * 64, st));
     return 0;
 }
 
@@ -442,7 +390,8 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
     for (int p = 0; p < PASSES; ++p) {
         if (skip[p]) continue;
         int rc;
-        switch (ws.cfg) {
+        if (ws.cfg >= TMA_CFG_BASE) rc = launch_tma_sweep(ws.cfg, src, dst, n, p, ws, st);
+        else switch (ws.cfg) {
             case 1: rc = launch_sweep<512, 16, 2>(src, dst, n, p, ws, st); break;
             case 2: rc = launch_sweep<256, 24, 2>(src, dst, n, p, ws, st); break;
             case 3: rc = launch_sweep<384, 16, 2>(src, dst, n, p, ws, st); break;

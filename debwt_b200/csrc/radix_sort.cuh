@@ -10,6 +10,7 @@ struct SortWorkspace {
     u32* tile_counter = nullptr;  // [8] dynamic tile ids, one per pass
     u32* skip = nullptr;          // [8] pass has a constant digit
     u64* lookback = nullptr;      // [ntiles][256] decoupled look-back words
+    u64* lookback_par = nullptr;  // [ntiles][8] look-back words of the count PARITIES (bulk-store kernel, radix_sort_tma.cu)
     u64 ntiles = 0;
     cudaEvent_t ev_sweep_begin = nullptr, ev_sweep_end = nullptr;   // optional: bracket the scatter passes
     int* sweeps_out = nullptr;                                        // optional: number of passes launched

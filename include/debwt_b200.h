@@ -48,6 +48,9 @@ typedef struct debwt_stats {
     uint32_t sort_launches;  /* kernel launches inside the sort phase */
     uint32_t sort_sweeps;    /* onesweep_kernel launches (8 unless a digit is constant) */
     uint32_t total_launches; /* kernel launches inside debwt_build() */
+    uint32_t reserved_;
+    uint64_t arena_bytes;      /* HBM held by the context's arena after the build (peak of the build) */
+    uint64_t arena_used_bytes; /* of which in use at the high-water mark */
 } debwt_stats;
 
 const char* debwt_last_error(void);
@@ -109,6 +112,9 @@ int debwt_k_group_masks(int device, const char* text, uint64_t n_symbols, const 
 /* Device-resident sort benchmark helper: sorts `n` pseudo-random keys `iters` times on the device
    (keys regenerated on device before each run) and returns the mean device ms per sort. */
 int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out);
+/* Same, and also the mean device ms of ONE digit pass (the named roofline kernel: 16 B/key algorithmic per launch),
+   from CUDA events around the scatter passes. */
+int debwt_bench_sort_passes(int device, uint64_t n, int cfg, int iters, float* ms_out, float* ms_per_pass_out);
 
 #ifdef __cplusplus
 }

@@ -39,8 +39,11 @@ def test_pack_rejects_non_acgt():
 
 
 # ---- K3 --------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
-@pytest.mark.parametrize("n", [0, 1, 2, 255, 4095, 4096, 4097, 100_000, 1_000_003])
+TMA_CFGS = [32, 33]       # radix_sort_tma.cu: bulk-store write-out (parity chain), two tile shapes
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9] + TMA_CFGS)
+@pytest.mark.parametrize("n", [0, 1, 2, 255, 3839, 3840, 3841, 4095, 4096, 4097, 100_000, 1_000_003])
 def test_radix_sort_random(cfg, n):
     rng = np.random.default_rng(n + cfg)
     keys = rng.integers(0, 2**64, size=n, dtype=np.uint64)
@@ -48,9 +51,10 @@ def test_radix_sort_random(cfg, n):
     assert (out == np.sort(keys)).all()
 
 
+@pytest.mark.parametrize("cfg", [0, 8, 32, 33])
 @pytest.mark.parametrize("kind", ["all_equal", "few_distinct", "sorted", "reversed", "low_bits_only", "high_bits_only", "dup_heavy"])
-def test_radix_sort_structured(kind):
-    n = 300_000
+def test_radix_sort_structured(kind, cfg):
+    n = 300_001
     rng = np.random.default_rng(7)
     if kind == "all_equal":
         keys = np.full(n, 0xDEADBEEF12345678, dtype=np.uint64)
@@ -66,7 +70,7 @@ def test_radix_sort_structured(kind):
         keys = rng.integers(0, 2**16, size=n, dtype=np.uint64) << np.uint64(48)
     else:
         keys = rng.integers(0, 2**64, size=n // 100, dtype=np.uint64)[rng.integers(0, n // 100, size=n)]
-    out, _ = api.k_radix_sort(keys)
+    out, _ = api.k_radix_sort(keys, cfg=cfg)
     assert (out == np.sort(keys)).all()
 
 
