@@ -119,6 +119,38 @@ class BwtBuilder:
         check(lib().debwt_result_copy(self._h, c_p(host_ptr), _ptr(sharp), _ptr(dollar)))
         return sharp, dollar
 
+    # -- FM-index tables / verifier (reference "developer mode", src/insertCase3.c:139-208, src/LFsearch.c) ----
+    def index(self):
+        """(occ[(N>>5)+1][4], C[6]) in the reference's layout, built on the device"""
+        check(lib().debwt_index_build(self._h))
+        rows = c_u64()
+        check(lib().debwt_index_sizes(self._h, ctypes.byref(rows)))
+        occ = np.empty((rows.value, 4), dtype=np.uint64)
+        carr = np.empty(6, dtype=np.uint64)
+        check(lib().debwt_index_copy(self._h, _ptr(occ), _ptr(carr)))
+        return occ, carr
+
+    def count(self, patterns: Sequence) -> np.ndarray:
+        """occurrences of each ACGT pattern in T, by backward search on the device"""
+        check(lib().debwt_index_build(self._h))
+        pats = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
+        offs = np.zeros(len(pats) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(p) for p in pats])
+        blob = np.frombuffer(b"".join(pats) + b"\0", dtype=np.uint8)
+        out = np.zeros(len(pats), dtype=np.uint64)
+        check(lib().debwt_index_count(self._h, _ptr(blob), _ptr(offs), len(pats), _ptr(out)))
+        return out
+
+    def verify(self, text=None, device_ptr: int | None = None, n_symbols: int | None = None):
+        """LF-inversion check of the last build against T; returns (bad rows, device ms).  0 bad rows <=> BWT(T)."""
+        bad, ms = c_u64(), ctypes.c_float()
+        if device_ptr is not None:
+            check(lib().debwt_verify_text_device(self._h, c_p(device_ptr), n_symbols, ctypes.byref(bad), ctypes.byref(ms)))
+        else:
+            text = np.ascontiguousarray(text, dtype=np.uint8)
+            check(lib().debwt_verify_text(self._h, _ptr(text), text.size, ctypes.byref(bad), ctypes.byref(ms)))
+        return int(bad.value), float(ms.value)
+
     def stats(self) -> dict:
         s = Stats()
         check(lib().debwt_get_stats(self._h, ctypes.byref(s)))

@@ -47,6 +47,15 @@ _SIGS = {
     "debwt_result_sizes": (ctypes.c_int, [c_p, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
     "debwt_result_copy": (ctypes.c_int, [c_p, c_p, c_p, c_p]),
     "debwt_get_stats": (ctypes.c_int, [c_p, ctypes.POINTER(Stats)]),
+    "debwt_index_build": (ctypes.c_int, [c_p]),
+    "debwt_index_sizes": (ctypes.c_int, [c_p, ctypes.POINTER(c_u64)]),
+    "debwt_index_copy": (ctypes.c_int, [c_p, c_p, c_p]),
+    "debwt_index_count": (ctypes.c_int, [c_p, c_p, c_p, c_u64, c_p]),
+    "debwt_verify_text": (ctypes.c_int, [c_p, c_p, c_u64, ctypes.POINTER(c_u64), ctypes.POINTER(ctypes.c_float)]),
+    "debwt_verify_text_device": (ctypes.c_int, [c_p, c_p, c_u64, ctypes.POINTER(c_u64), ctypes.POINTER(ctypes.c_float)]),
+    "debwt_synth_random_bases": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_u64]),
+    "debwt_synth_insert_family": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_u64, c_u64, c_u64, c_u64, c_p]),
+    "debwt_synth_mutate": (ctypes.c_int, [ctypes.c_int, c_p, c_p, c_u64, c_u64, c_u64]),
     "debwt_k_pack": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_p]),
     "debwt_k_extract": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_p, c_u64, c_p]),
     "debwt_k_radix_sort_u64": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),

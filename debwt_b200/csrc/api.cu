@@ -19,6 +19,7 @@
 #include "radix_sort.cuh"
 #include "stages.cuh"
 #include "special.cuh"
+#include "ctx.cuh"
 
 namespace debwt {
 
@@ -32,74 +33,6 @@ void set_error(const std::string& msg) { g_err = msg; }
         debwt::set_error(msg); \
         return -1;           \
     } while (0)
-
-// ---------------------------------------------------------------------------------------------
-// device memory: a per-context arena (grow-only chunks, bump allocation, reset per build).  The driver's
-// stream-ordered pool (cudaMallocAsync) showed millisecond-level, step-to-step variance for the
-// multi-hundred-MB buffers of a build; an arena makes steady-state builds allocation-free.
-// ---------------------------------------------------------------------------------------------
-struct DevPool {
-    struct Chunk { char* base; size_t cap, used; bool owned; };
-    cudaStream_t st = nullptr;
-    std::vector<Chunk> chunks;          // adopted (borrowed) regions first, then the chunks this pool cudaMalloc'ed
-    size_t next_chunk = 256ull << 20;
-    void hint(size_t bytes) { if (bytes > next_chunk) next_chunk = bytes; }
-    int alloc(void** p, size_t bytes) {
-        bytes = (bytes + 511) & ~(size_t)511;
-        if (bytes == 0) bytes = 512;
-        for (auto& c : chunks) {
-            if (c.cap - c.used >= bytes) { *p = c.base + c.used; c.used += bytes; return 0; }
-        }
-        Chunk c{nullptr, bytes > next_chunk ? bytes : next_chunk, 0, true};
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c.base), c.cap));
-        *p = c.base;
-        c.used = bytes;
-        chunks.push_back(c);
-        return 0;
-    }
-    // A buffer of this pool that the build no longer needs (the ping-pong half the sort did not end in, the ASCII text
-    // after packing) becomes a region later allocations are served from first.  It stays reserved in its own chunk,
-    // so nothing is handed out twice; adopted regions vanish at the next rewind.
-    void adopt(void* p, size_t bytes) {
-        char* q = static_cast<char*>(p);
-        char* a = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(q) + 511) & ~(uintptr_t)511);
-        if (!p || a >= q + bytes) return;
-        const size_t cap = (size_t)(q + bytes - a) & ~(size_t)511;
-        if (cap) chunks.insert(chunks.begin(), Chunk{a, cap, 0, false});
-    }
-    // state of the owned chunks (bytes in use), to come back to before a build
-    std::vector<size_t> mark() const {
-        std::vector<size_t> m;
-        for (auto& c : chunks) if (c.owned) m.push_back(c.used);
-        return m;
-    }
-    void rewind(const std::vector<size_t>& m) {
-        std::vector<Chunk> keep;
-        size_t i = 0;
-        for (auto& c : chunks) {
-            if (!c.owned) continue;
-            c.used = i < m.size() ? m[i] : 0;
-            ++i;
-            keep.push_back(c);
-        }
-        chunks.swap(keep);
-    }
-    void release_all() { rewind({}); }
-    size_t reserved_bytes() const {             // HBM this pool holds
-        size_t t = 0;
-        for (auto& c : chunks) if (c.owned) t += c.cap;
-        return t;
-    }
-    size_t used_bytes() const {                 // high-water marks of the owned chunks (adopted regions live inside them)
-        size_t t = 0;
-        for (auto& c : chunks) if (c.owned) t += c.used;
-        return t;
-    }
-    void destroy() {
-        for (auto& c : chunks) if (c.owned) cudaFree(c.base);
-        chunks.clear();
-    }
-};
 
 template <typename T>
 static int dalloc(DevPool& pool, T** p, size_t count) { return pool.alloc(reinterpret_cast<void**>(p), count * sizeof(T)); }
@@ -115,7 +48,6 @@ struct Special {
 };
 
 constexpr u64 kMaxDeviceSpecials = 16384;   // 32 R above this: host sort (all-pairs ranking is quadratic)
-constexpr int kDefaultSortCfg = 8;          // 384 threads x 16 keys per tile, 3 CTAs/SM
 
 
 // Host part of the sentinel-window handling: from the per-suffix scan results (rank, windows, insertion
@@ -171,28 +103,6 @@ int build_special_tables(const SpecialInfo* info, const u64* seps, u64 R, std::v
 
 using namespace debwt;
 
-struct debwt_ctx {
-    int device = 0;
-    int sort_cfg = kDefaultSortCfg;
-    cudaStream_t st = nullptr;
-    DevPool pool;
-    // input
-    u64 n = 0, n_rec = 0;
-    std::vector<u64> seps;
-    u8* d_ascii = nullptr;         // owned unless external
-    const u8* d_ascii_ext = nullptr;
-    // result
-    u64* d_bwt = nullptr;
-    u64* d_sharp = nullptr;
-    u32* d_sharp_count = nullptr;
-    u64* d_dollar = nullptr;
-    u64 n_words = 0;
-    bool built = false;
-    std::vector<size_t> input_mark;   // pool state right after the input was set: every build starts from here
-    debwt_stats stats{};
-    cudaEvent_t ev[16]{};
-};
-
 namespace {
 
 std::mutex g_pool_mutex;
@@ -239,6 +149,7 @@ int check_seps(const T* seps, u64 n_rec, u64 n) {
 }
 
 void reset_input(debwt_ctx* c) {
+    drop_index(c);
     c->pool.release_all();
     c->input_mark.clear();
     c->d_ascii = nullptr;
@@ -286,6 +197,7 @@ void debwt_destroy(debwt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
+    drop_index(c);
     c->pool.destroy();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->st);
@@ -375,6 +287,7 @@ int debwt_build(debwt_ctx* c, int k) {
     cudaStream_t st = c->st;
     DevPool& pool = c->pool;
     pool.rewind(c->input_mark);          // a repeated build on the same (device-resident) input reuses the arena
+    drop_index(c);
     c->built = false;
     const u64 n = c->n, R = c->n_rec, nk = n - 32 * R;
     debwt_stats& S = c->stats;

@@ -700,6 +700,11 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
         WorkItem* lists = nullptr;
         u32* d_cnt = nullptr;
         u64* g_key = nullptr;
+        struct AsyncFree {                  // the work lists live outside the build arena: hand them back on every exit path
+            cudaStream_t st;
+            void** p[3];
+            ~AsyncFree() { for (void** q : p) if (*q) cudaFreeAsync(*q, st); }
+        } guard{st, {reinterpret_cast<void**>(&lists), reinterpret_cast<void**>(&d_cnt), reinterpret_cast<void**>(&g_key)}};
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lists), 2 * per_set * sizeof(WorkItem), st));
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), 64, st));
         if (h[3]) CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g_key), bt.n_blue * 12 + 64, st));
@@ -712,7 +717,9 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
         if (h[3]) seed_items_kernel<<<(h[3] + TPB - 1) / TPB, TPB, 0, st>>>(bt, huge, h[3], cur);
         launched += (h[2] ? 1 : 0) + (h[3] ? 1 : 0);
         u32 n_cur[3] = {1, h[3], 1};                      // exact small/tiny counts are on the device
-        for (int round = 0; (n_cur[0] || n_cur[1] || n_cur[2]) && round < 100000; ++round) {
+        constexpr int kMaxRounds = 100000;
+        int round = 0;
+        for (; (n_cur[0] || n_cur[1] || n_cur[2]) && round < kMaxRounds; ++round) {
             CUDA_TRY(cudaMemsetAsync(nxt.cnt, 0, 16, st));
             if (n_cur[1]) {
                 const u32 grid = 148u * 2u;
@@ -728,9 +735,6 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
             const u32* c = cur.cnt == d_cnt ? n_fin : n_fin + 4;
             const u32* n = cur.cnt == d_cnt ? n_fin + 4 : n_fin;
             if (c[0] > cap_small || c[2] > cap_tiny || n[0] > cap_small || n[1] > cap_huge || n[2] > cap_tiny) {
-                cudaFreeAsync(lists, st);
-                cudaFreeAsync(d_cnt, st);
-                if (g_key) cudaFreeAsync(g_key, st);
                 set_error("internal: K10 work list overflow");
                 return -1;
             }
@@ -740,9 +744,10 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
             n_cur[0] = n[0]; n_cur[1] = n[1]; n_cur[2] = n[2];
             WorkLists t = cur; cur = nxt; nxt = t;
         }
-        CUDA_TRY(cudaFreeAsync(lists, st));
-        CUDA_TRY(cudaFreeAsync(d_cnt, st));
-        if (g_key) CUDA_TRY(cudaFreeAsync(g_key, st));
+        if (n_cur[0] || n_cur[1] || n_cur[2]) {
+            set_error("K10: segmented sort did not finish within the round limit (work items remain)");
+            return -1;
+        }
     }
     DEBWT_COUNT(launched);
     CUDA_TRY(cudaGetLastError());

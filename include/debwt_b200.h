@@ -92,6 +92,35 @@ int debwt_result_sizes(const debwt_ctx* ctx, uint64_t* n_symbols, uint64_t* n_wo
 int debwt_result_copy(debwt_ctx* ctx, uint64_t* bwt_words, uint64_t* sharp_rows, uint64_t* dollar_row);
 int debwt_get_stats(const debwt_ctx* ctx, debwt_stats* out);
 
+/* ---- FM-index tables over the result: the reference's "developer mode", src/insertCase3.c:139-208 ---------- */
+/* occ checkpoints every 32 rows in the reference's layout -- occ[(N >> 5) + 1][4] u64, occ[w][c] = rows < 32 w holding
+   base c, rows holding '#'/'$' (stored as T) not counted -- and the C-array (src/collect#$.c:92-100).  Built on the
+   device from the result of debwt_build(); kept until the next build / input. */
+int debwt_index_build(debwt_ctx* ctx);
+int debwt_index_sizes(const debwt_ctx* ctx, uint64_t* occ_rows);
+/* occ: occ_rows * 4 u64 (may be NULL); c_array: 6 u64 = first row of the suffixes starting with A, C, G, T, '#', '$' */
+int debwt_index_copy(debwt_ctx* ctx, uint64_t* occ, uint64_t* c_array);
+/* Backward search (count only) of n_patterns ACGT strings on the device; pattern i = patterns[offsets[i] .. offsets[i+1]).
+   Uses occ / C the way findSeg does (src/LFsearch.c:167-235). */
+int debwt_index_count(debwt_ctx* ctx, const char* patterns, const uint64_t* offsets, uint64_t n_patterns, uint64_t* counts);
+/* At-scale verifier: inverts the BWT by its LF mapping (the walk of src/LFsearch.c:49-166, as parallel list ranking) and
+   compares every symbol with the text T given by the caller (ASCII, '#' between records, '$' last; host or device
+   pointer).  *n_bad_out = rows that are not on the one N-cycle or whose symbol differs; 0 <=> the result is the BWT of
+   T.  Needs 16 bytes of scratch HBM per symbol; N < 2^32 - 1. */
+int debwt_verify_text(debwt_ctx* ctx, const char* text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out);
+int debwt_verify_text_device(debwt_ctx* ctx, const void* d_text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out);
+
+/* ---- synthetic workloads on the device (bench / test plumbing; bit-identical to debwt_b200/synth.py) ------ */
+/* n iid-uniform bases (ASCII) of the splitmix64 stream `seed` into device memory */
+int debwt_synth_random_bases(int device, void* d_out, uint64_t n, uint64_t seed);
+/* one repeat family written over d_seq (n bases): `copies` copies of a `length`-base master at pseudo-random offsets,
+   each with substitutions at threshold `thr` = int(rate * 2^53) (0 = exact copies); later copies overwrite earlier ones.
+   d_owner_zeroed: n u32 of zeroed scratch (left zeroed). */
+int debwt_synth_insert_family(int device, void* d_seq, uint64_t n, uint64_t seed, uint64_t copies, uint64_t length, uint64_t thr,
+                              void* d_owner_zeroed);
+/* d_out = d_in with iid substitutions (never to the same base) at threshold `thr` */
+int debwt_synth_mutate(int device, const void* d_in, void* d_out, uint64_t n, uint64_t seed, uint64_t thr);
+
 /* ---- per-kernel entry points (host buffers in, host buffers out) for parity tests -------------- */
 /* K1: ASCII text -> 2-bit packed words, ceil((n+32)/32) of them (src/collect#$.c:78-90). */
 int debwt_k_pack(int device, const char* text, uint64_t n_symbols, uint64_t* words_out);

@@ -25,9 +25,19 @@ def test_library_exports_every_device_stage_symbol():
         assert hasattr(L, n), n
 
 
-def test_stats_struct_matches_header_layout():
-    # 7 u64 + 12 float + 3 u32 = 56 + 48 + 12 = 116 -> padded to 120
-    assert ctypes.sizeof(binding.Stats) == 120
+def test_stats_struct_matches_header_layout(tmp_path):
+    """the ctypes mirror has the size and field offsets a C compiler gives include/debwt_b200.h"""
+    import os
+    import subprocess
+    src = tmp_path / "sz.c"
+    fields = [n for n, _ in binding.Stats._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "debwt_b200.h"\nint main(void){printf("%zu", sizeof(debwt_stats));'
+                   + "".join('printf(" %%zu", offsetof(debwt_stats, %s));' % f for f in fields) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.dirname(binding.HEADER), "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(binding.Stats)
+    assert out[1:] == [getattr(binding.Stats, f).offset for f in fields]
 
 
 def test_no_cpu_fallback_without_device():
