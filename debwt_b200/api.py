@@ -223,3 +223,12 @@ def bench_sort_passes(n: int, device: int = 0, cfg: int = 0, iters: int = 5):
     ms, msp = ctypes.c_float(), ctypes.c_float()
     check(lib().debwt_bench_sort_passes(device, n, cfg, iters, ctypes.byref(ms), ctypes.byref(msp)))
     return ms.value, msp.value
+
+
+def verify_bwt_device(bwt_ptr: int, n_symbols: int, sharp_rows: np.ndarray, dollar_row: int, text_ptr: int, device: int = 0):
+    """LF-inversion check of a packed BWT in device memory against the ASCII text in device memory: (bad rows, ms)"""
+    sharp = np.ascontiguousarray(sharp_rows, dtype=np.uint64)
+    bad, ms = c_u64(), ctypes.c_float()
+    check(lib().debwt_verify_bwt_device(device, c_p(bwt_ptr), n_symbols, _ptr(sharp), sharp.size, int(dollar_row), c_p(text_ptr),
+                                        ctypes.byref(bad), ctypes.byref(ms)))
+    return int(bad.value), float(ms.value)

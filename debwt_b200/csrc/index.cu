@@ -238,29 +238,20 @@ using namespace debwt;
 
 extern "C" {
 
-int debwt_index_build(debwt_ctx* c) {
-    if (!c || !c->built) FAIL("no result: call debwt_build first");
-    if (c->indexed) return 0;
-    CUDA_TRY(cudaSetDevice(c->device));
+// sharp: the rows holding '#', ascending
+static int index_build_with(debwt_ctx* c, std::vector<u64> sharp, u64 dollar_row) {
     cudaStream_t st = c->st;
-    const u64 n = c->n, nwords = c->n_words, n_sharp = c->n_rec - 1, occ_len = (n >> 5) + 1;
-    // separator rows: '#' rows sorted (src/insertCase3.c:84-95 writes them ascending), '$' row
-    std::vector<u64> sharp(c->n_rec + 1);
-    u32 cnt = 0;
-    CUDA_TRY(cudaMemcpyAsync(&cnt, c->d_sharp_count, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(&c->dollar_row, c->d_dollar, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(sharp.data(), c->d_sharp, (c->n_rec + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (cnt != n_sharp) FAIL("internal: wrong number of '#' rows");
-    std::sort(sharp.begin(), sharp.begin() + cnt);
-    sharp[cnt] = c->dollar_row;                                                   // all special rows: cnt + 1 entries
+    const u64 n = c->n, nwords = c->n_words, occ_len = (n >> 5) + 1;
+    const u64 cnt = sharp.size();
+    c->dollar_row = dollar_row;
+    sharp.push_back(dollar_row);                                                  // all special rows: cnt + 1 entries
     drop_index(c);
     const u64 nb = (nwords + TPB - 1) / TPB;
     u32* d_tot = nullptr;
     u64 *d_base = nullptr, *d_totals = nullptr;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_occ), (occ_len + 1) * 32));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_spec_bits), (nwords + 1) * 4));
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_sharp_sorted), (c->n_rec + 1) * 8));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&c->d_sharp_sorted), (cnt + 1) * 8));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_tot), nb * 16 + 16));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_base), nb * 32 + 64));
     d_totals = d_base + nb * 4;
@@ -286,6 +277,25 @@ int debwt_index_build(debwt_ctx* c) {
     c->c_array[5] = n - 1;                                                        // '$'
     c->indexed = true;
     return 0;
+}
+
+int debwt_index_build(debwt_ctx* c) {
+    if (!c || !c->built) FAIL("no result: call debwt_build first");
+    if (c->indexed) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->st;
+    // separator rows: '#' rows sorted (src/insertCase3.c:84-95 writes them ascending), '$' row
+    std::vector<u64> sharp(c->n_rec + 1);
+    u32 cnt = 0;
+    u64 dollar = 0;
+    CUDA_TRY(cudaMemcpyAsync(&cnt, c->d_sharp_count, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&dollar, c->d_dollar, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(sharp.data(), c->d_sharp, (c->n_rec + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (cnt != c->n_rec - 1) FAIL("internal: wrong number of '#' rows");
+    sharp.resize(cnt);
+    std::sort(sharp.begin(), sharp.end());
+    return index_build_with(c, std::move(sharp), dollar);
 }
 
 int debwt_index_sizes(const debwt_ctx* c, uint64_t* occ_rows) {
@@ -323,11 +333,8 @@ int debwt_index_count(debwt_ctx* c, const char* patterns, const uint64_t* offset
     return 0;
 }
 
-int debwt_verify_text_device(debwt_ctx* c, const void* d_text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out) {
-    if (!c || !c->built) FAIL("no result: call debwt_build first");
-    if (n_symbols != c->n) FAIL("verify: text length differs from the build's");
+static int verify_indexed(debwt_ctx* c, const void* d_text, uint64_t* n_bad_out, float* ms_out) {
     if (c->n >= 0xFFFFFFFFull) FAIL("verify: N must be below 2^32 - 1");
-    if (debwt_index_build(c)) return -1;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->st;
     const u64 n = c->n;
@@ -373,6 +380,34 @@ int debwt_verify_text_device(debwt_ctx* c, const void* d_text, uint64_t n_symbol
     if (n_bad_out) *n_bad_out = bad;
     if (ms_out) *ms_out = ms;
     return 0;
+}
+
+int debwt_verify_text_device(debwt_ctx* c, const void* d_text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out) {
+    if (!c || !c->built) FAIL("no result: call debwt_build first");
+    if (n_symbols != c->n) FAIL("verify: text length differs from the build's");
+    if (debwt_index_build(c)) return -1;
+    return verify_indexed(c, d_text, n_bad_out, ms_out);
+}
+
+int debwt_verify_bwt_device(int device, const uint64_t* d_bwt_words, uint64_t n_symbols, const uint64_t* sharp_rows, uint64_t n_sharp,
+                            uint64_t dollar_row, const void* d_text, uint64_t* n_bad_out, float* ms_out) {
+    if (!d_bwt_words || !d_text || (n_sharp && !sharp_rows)) FAIL("null argument");
+    if (debwt_device_count() <= device || device < 0) FAIL("no such CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    debwt_ctx tmp;                                        // a view of the caller's buffers, nothing owned but the index
+    tmp.device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&tmp.st, cudaStreamNonBlocking));
+    tmp.n = n_symbols; tmp.n_rec = n_sharp + 1; tmp.n_words = (n_symbols + 31) / 32;
+    tmp.d_bwt = reinterpret_cast<u64*>(const_cast<uint64_t*>(d_bwt_words));
+    tmp.built = true;
+    std::vector<u64> sharp(sharp_rows, sharp_rows + n_sharp);
+    std::sort(sharp.begin(), sharp.end());
+    CUDA_TRY(cudaDeviceSynchronize());                    // the caller's buffers may have been produced on another stream
+    int rc = index_build_with(&tmp, std::move(sharp), dollar_row);
+    if (!rc) rc = verify_indexed(&tmp, d_text, n_bad_out, ms_out);
+    drop_index(&tmp);
+    cudaStreamDestroy(tmp.st);
+    return rc;
 }
 
 int debwt_verify_text(debwt_ctx* c, const char* text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out) {

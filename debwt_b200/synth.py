@@ -127,6 +127,27 @@ def genome_like(n: int, seed0: int, scale: float = 1.0) -> np.ndarray:
     return seq
 
 
+def genome_like_prefix(n: int, seed0: int, m: int, scale: float = 1.0) -> np.ndarray:
+    """the first m bases of genome_like(n, seed0, scale) without generating the other n - m: the background is indexed by
+    position, and only the copies of each family that reach into [0, m) are applied (in copy order, as _insert_family does).
+    Used by the CPU arms of bench.py, which run the reference on a bounded prefix of a multi-Gbp workload."""
+    m = min(m, n)
+    seq = random_bases(seed0, m)
+    f = n / 3.1e9 * scale
+    for seed, copies, length, rate in ((seed0 + 1, int(1_000_000 * f), 300, 0.10), (seed0 + 2, int(100_000 * f), 6000, 0.03),
+                                       (seed0 + 3, int(2_000 * f), 10_000, 0.0)):
+        if copies <= 0 or n <= length:
+            continue
+        master = random_bases(seed, length)
+        offs = _rand_ints(seed + (1 << 33), copies, n - length)
+        for i in np.flatnonzero(offs < m).tolist():              # ascending copy index: later copies overwrite earlier ones
+            o = int(offs[i])
+            el = master if rate == 0.0 else _mutate_many(master, np.array([i + seed + (1 << 34)], dtype=np.uint64), rate)[0]
+            k = min(length, m - o)
+            seq[o:o + k] = el[:k]
+    return seq
+
+
 def config3(n: int = 3_100_000_000, n_records: int = 24):
     """C3: human-sized genome split into `n_records` records (each < 2^31 bp)."""
     seq = genome_like(n, 5)

@@ -109,6 +109,11 @@ int debwt_index_count(debwt_ctx* ctx, const char* patterns, const uint64_t* offs
    T.  Needs 16 bytes of scratch HBM per symbol; N < 2^32 - 1. */
 int debwt_verify_text(debwt_ctx* ctx, const char* text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out);
 int debwt_verify_text_device(debwt_ctx* ctx, const void* d_text, uint64_t n_symbols, uint64_t* n_bad_out, float* ms_out);
+/* The same check for a packed BWT that is not a context's result (e.g. the stitched output of the sharded build):
+   d_bwt_words / d_text are device pointers on `device`, sharp_rows (host, any order) and dollar_row as written to the
+   reference's .# / .$ files. */
+int debwt_verify_bwt_device(int device, const uint64_t* d_bwt_words, uint64_t n_symbols, const uint64_t* sharp_rows, uint64_t n_sharp,
+                            uint64_t dollar_row, const void* d_text, uint64_t* n_bad_out, float* ms_out);
 
 /* ---- synthetic workloads on the device (bench / test plumbing; bit-identical to debwt_b200/synth.py) ------ */
 /* n iid-uniform bases (ASCII) of the splitmix64 stream `seed` into device memory */
