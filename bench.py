@@ -517,6 +517,12 @@ def ours_sharded(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, wall_ms = (float(x) for x in tt.tolist())
+    phases = None
+    if args.profile_phases:                              # one extra, synchronised step: per-phase wall times on rank 0 (not a timing run)
+        stats["profile"] = True
+        step(True)
+        phases = stats.get("phases_ms")
+        stats["profile"] = False
     if rank == 0:
         sha = hashlib.sha256(h_out.numpy().tobytes()).hexdigest()
         want = expected_sha(w.name)
@@ -552,6 +558,8 @@ def ours_sharded(args, rank, world, local_rank):
             "verify": verify,
             "bwt_sha256": sha,
         }
+        if phases:
+            line["rank0_phases_ms_synchronised"] = phases
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -571,6 +579,7 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the LF-inversion verifier in the epilogue")
     ap.add_argument("--no-file-to-file", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks (to measure the sampler's own cost)")
+    ap.add_argument("--profile-phases", action="store_true", help="sharded path: add rank 0's synchronised per-phase times")
     ap.add_argument("--sharded", action="store_true", help="use the sharded (multi-GPU) code path even at N=1")
     args = ap.parse_args()
     if args.no_clocks:

@@ -97,6 +97,16 @@ class BwtBuilder:
         self._keep = seps
         check(lib().debwt_set_text_device(self._h, c_p(device_ptr), n_symbols, _ptr(seps), seps.size))
 
+    def ingest(self, chunks, seps: np.ndarray, n_hint: int = 0):
+        """Streaming input (debwt_ingest_*): `chunks` yields consecutive pieces of T as bytes / uint8 arrays"""
+        seps = np.ascontiguousarray(seps, dtype=np.uint64)
+        check(lib().debwt_ingest_begin(self._h, n_hint))
+        for ch in chunks:
+            a = np.ascontiguousarray(np.frombuffer(ch, dtype=np.uint8) if not isinstance(ch, np.ndarray) else ch, dtype=np.uint8)
+            if a.size:
+                check(lib().debwt_ingest_append(self._h, _ptr(a), a.size))
+        check(lib().debwt_ingest_end(self._h, _ptr(seps), seps.size))
+
     # -- build / output -------------------------------------------------------------------------
     def build(self, k: int = 32):
         check(lib().debwt_build(self._h, k))

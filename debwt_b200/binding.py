@@ -43,6 +43,13 @@ _SIGS = {
     "debwt_set_records": (ctypes.c_int, [c_p, ctypes.POINTER(c_p), ctypes.POINTER(c_u64), c_u64]),
     "debwt_set_text": (ctypes.c_int, [c_p, c_p, c_u64, c_p, c_u64]),
     "debwt_set_text_device": (ctypes.c_int, [c_p, c_p, c_u64, c_p, c_u64]),
+    "debwt_ingest_begin": (ctypes.c_int, [c_p, c_u64]),
+    "debwt_ingest_reserve": (ctypes.c_int, [c_p, ctypes.POINTER(c_p), ctypes.POINTER(c_u64)]),
+    "debwt_ingest_commit": (ctypes.c_int, [c_p, c_u64]),
+    "debwt_ingest_append": (ctypes.c_int, [c_p, c_p, c_u64]),
+    "debwt_ingest_end": (ctypes.c_int, [c_p, c_p, c_u64]),
+    "debwt_host_alloc": (c_p, [c_u64]),
+    "debwt_host_free": (None, [c_p]),
     "debwt_build": (ctypes.c_int, [c_p, ctypes.c_int]),
     "debwt_result_sizes": (ctypes.c_int, [c_p, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
     "debwt_result_copy": (ctypes.c_int, [c_p, c_p, c_p, c_p]),

@@ -8,6 +8,7 @@
 //   sortBlue          -> K10 segmented sort
 //   insertCase3       -> K8 case-2 fill, K11 case-3 / special emission
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
@@ -20,6 +21,7 @@
 #include "stages.cuh"
 #include "special.cuh"
 #include "ctx.cuh"
+#include "dist_kernels.cuh"
 
 namespace debwt {
 
@@ -47,7 +49,6 @@ struct Special {
     bool emit;
 };
 
-constexpr u64 kMaxDeviceSpecials = 16384;   // 32 R above this: host sort (all-pairs ranking is quadratic)
 
 
 // Host part of the sentinel-window handling: from the per-suffix scan results (rank, windows, insertion
@@ -154,6 +155,9 @@ void reset_input(debwt_ctx* c) {
     c->input_mark.clear();
     c->d_ascii = nullptr;
     c->d_ascii_ext = nullptr;
+    c->d_packed = nullptr;
+    c->d_packed_err = nullptr;
+    c->ing.active = false;
     c->d_bwt = nullptr;
     c->d_sharp = nullptr;
     c->d_sharp_count = nullptr;
@@ -198,6 +202,10 @@ void debwt_destroy(debwt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     drop_index(c);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ing.h_stage[i]) cudaFreeHost(c->ing.h_stage[i]);
+        if (c->ing.done[i]) cudaEventDestroy(c->ing.done[i]);
+    }
     c->pool.destroy();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->st);
@@ -283,7 +291,8 @@ int debwt_build(debwt_ctx* c, int k) {
     if (c->n == 0) FAIL("no input set");
     if (bind_device(c->device)) return -1;
     const u8* ascii = c->d_ascii_ext ? c->d_ascii_ext : c->d_ascii;
-    if (!ascii) FAIL("input was consumed by a previous build; set it again");
+    if (c->ing.active) FAIL("streaming input is still open: call debwt_ingest_end first");
+    if (!ascii && !c->d_packed) FAIL("input was consumed by a previous build; set it again");
     cudaStream_t st = c->st;
     DevPool& pool = c->pool;
     pool.rewind(c->input_mark);          // a repeated build on the same (device-resident) input reuses the arena
@@ -302,11 +311,17 @@ int debwt_build(debwt_ctx* c, int k) {
 
     // ---- K1 pack ----
     u64* d_seps = nullptr; u64* d_text = nullptr; u32* d_err = nullptr;
-    if (dalloc(pool, &d_seps, R) || dalloc(pool, &d_text, text_words(n)) || dalloc(pool, &d_err, 4)) return -1;
+    if (dalloc(pool, &d_seps, R)) return -1;
     CUDA_TRY(cudaMemcpyAsync(d_seps, c->seps.data(), R * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
-    if (k_pack(ascii, n, d_text, d_err, st)) return -1;
-    if (c->d_ascii) { pool.adopt(c->d_ascii, n + 64); c->d_ascii = nullptr; }
+    if (c->d_packed) {                   // streamed in and packed chunk by chunk (debwt_ingest_*): K1 already ran
+        d_text = c->d_packed;
+        d_err = c->d_packed_err;
+    } else {
+        if (dalloc(pool, &d_text, text_words(n)) || dalloc(pool, &d_err, 4)) return -1;
+        CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
+        if (k_pack(ascii, n, d_text, d_err, st)) return -1;
+        if (c->d_ascii) { pool.adopt(c->d_ascii, n + 64); c->d_ascii = nullptr; }
+    }
     mark();                                                                     // ev1
 
     // ---- K2 extract ----
@@ -376,53 +391,24 @@ int debwt_build(debwt_ctx* c, int k) {
     if (k_branch_index(bt, st)) return -1;
     mark();                                                                     // ev4
 
-    // ---- sentinel-window suffixes: ranked on the device (32 R suffixes, all pairs), tables built on the host ----
+    // ---- sentinel-window suffixes: ranked on the device (all pairs for few records, a bitonic network beyond), tables
+    //      built on the host ----
     const u64 nspec = 32 * R;
     std::vector<SpecialInfo> info(nspec);
     std::vector<u64> h_ins(nspec);
     u64* d_ins = nullptr;
     if (dalloc(pool, &d_ins, nspec)) return -1;
-    if (nspec <= kMaxDeviceSpecials) {
+    {
         SpecialInfo* d_info = nullptr;
         if (dalloc(pool, &d_info, nspec)) return -1;
         if (k_special_scan(d_text, d_seps, R, d_keys, nk, ki, d_info, st)) return -1;
         CUDA_TRY(cudaMemcpyAsync(info.data(), d_info, nspec * sizeof(SpecialInfo), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-    } else {
-        // many records: sort on the host over a copy of the packed text (reference: qsort, src/collect#$.c:157)
-        std::vector<u64> h_text(text_words(n));
-        CUDA_TRY(cudaMemcpyAsync(h_text.data(), d_text, h_text.size() * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        std::vector<u32> order(nspec);
-        for (u64 t = 0; t < nspec; ++t) order[t] = (u32)t;
-        const u64* sp_seps = c->seps.data();
-        std::sort(order.begin(), order.end(), [&](u32 x, u32 y) {
-            return special_less(h_text.data(), sp_seps, R, sp_seps[x >> 5] - (x & 31), sp_seps[y >> 5] - (y & 31));
-        });
-        std::vector<u64> h_pads(nspec);
-        for (u64 i = 0; i < nspec; ++i) {
-            const u64 t = order[i], p = sp_seps[t >> 5] - (t & 31);
-            const u32 j = (u32)(t & 31);
-            SpecialInfo& o = info[t];
-            o.w0 = text_window32(h_text.data(), p);
-            o.w1 = text_window32(h_text.data(), p + j + 1);
-            o.rank = (u32)i;
-            o.prev = (u8)text_symbol(h_text.data(), p - 1);
-            o.next = (u8)text_symbol(h_text.data(), p + 31);
-            h_pads[t] = j ? ((o.w0 & ~(~0ull >> (2 * j))) | (~0ull >> (2 * j))) : ~0ull;
-        }
-        u64* d_pads = nullptr;
-        if (dalloc(pool, &d_pads, nspec)) return -1;
-        CUDA_TRY(cudaMemcpyAsync(d_pads, h_pads.data(), nspec * 8, cudaMemcpyHostToDevice, st));
-        if (k_special_insertion(d_keys, nk, ki, d_pads, nspec, d_ins, st)) return -1;
-        CUDA_TRY(cudaMemcpyAsync(h_ins.data(), d_ins, nspec * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        for (u64 t = 0; t < nspec; ++t) info[t].ins = (t & 31) ? h_ins[t] : nk;
     }
     std::vector<u64> h_rows, h_emit_pos, h_tail_pos;
     std::vector<u8> h_chr;
     if (build_special_tables(info.data(), c->seps.data(), R, h_ins, h_rows, h_chr, h_emit_pos, h_tail_pos)) return -1;
-    u64 *d_rows = nullptr, *d_emit = nullptr, *d_tail = nullptr, *d_tail_idx = nullptr, *d_pads = nullptr;
+    u64 *d_rows = nullptr, *d_emit = nullptr, *d_tail = nullptr, *d_tail_idx = nullptr;
     u8* d_chr = nullptr;
     if (dalloc(pool, &d_rows, nspec) || dalloc(pool, &d_chr, nspec) || dalloc(pool, &d_emit, h_emit_pos.size() + 1) ||
         dalloc(pool, &d_tail, R) || dalloc(pool, &d_tail_idx, R))
@@ -528,6 +514,139 @@ int debwt_result_copy(debwt_ctx* c, uint64_t* bwt_words, uint64_t* sharp_rows, u
 int debwt_get_stats(const debwt_ctx* c, debwt_stats* out) {
     if (!c || !out) FAIL("null argument");
     *out = c->stats;
+    return 0;
+}
+
+}  // extern "C"
+
+
+// ---- streaming ingest: replaces the two kseq passes of collect (src/collect#$.c:37-48, 66-86) -------------------
+namespace {
+constexpr u64 kStageBytes = 32ull << 20;
+
+// copy + pack what the current stage holds; final: also the T padding and the guard word
+int ingest_flush(debwt_ctx* c, bool final) {
+    auto& g = c->ing;
+    const u64 full = final ? g.fill : (g.fill & ~31ull);
+    if (full == 0 && !final) return 0;
+    const u64 nwords = final ? text_words(g.n + full) - g.n / 32 : full / 32;
+    if (g.n / 32 + nwords > g.cap_words) {                 // the hint was too small: move the packed text to a larger block
+        u64 cap = g.cap_words * 2;
+        while (cap < g.n / 32 + nwords) cap *= 2;
+        u64* bigger = nullptr;
+        if (dalloc(c->pool, &bigger, cap)) return -1;
+        CUDA_TRY(cudaMemcpyAsync(bigger, c->d_packed, (g.n / 32) * 8, cudaMemcpyDeviceToDevice, c->st));
+        c->d_packed = bigger;
+        g.cap_words = cap;
+    }
+    const int i = g.cur;
+    if (full) CUDA_TRY(cudaMemcpyAsync(g.d_stage[i], g.h_stage[i], full, cudaMemcpyHostToDevice, c->st));
+    if (k_pack_words(g.d_stage[i], full, c->d_packed + g.n / 32, nwords, c->d_packed_err, c->st)) return -1;
+    CUDA_TRY(cudaEventRecord(g.done[i], c->st));
+    g.busy[i] = true;
+    g.n += full;
+    if (!final) {                                          // carry the < 32 leftover symbols into the other stage
+        const u64 tail = g.fill - full;
+        const int o = i ^ 1;
+        if (g.busy[o]) { CUDA_TRY(cudaEventSynchronize(g.done[o])); g.busy[o] = false; }
+        if (tail) memcpy(g.h_stage[o], g.h_stage[i] + full, tail);
+        g.cur = o;
+        g.fill = tail;
+    } else {
+        g.fill = 0;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+void* debwt_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void debwt_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int debwt_ingest_begin(debwt_ctx* c, uint64_t n_symbols_hint) {
+    if (!c) FAIL("null context");
+    if (bind_device(c->device)) return -1;
+    reset_input(c);
+    auto& g = c->ing;
+    for (int i = 0; i < 2; ++i) {
+        if (!g.h_stage[i]) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g.h_stage[i]), kStageBytes, cudaHostAllocDefault));
+        if (!g.done[i]) CUDA_TRY(cudaEventCreateWithFlags(&g.done[i], cudaEventDisableTiming));
+        g.busy[i] = false;
+    }
+    const u64 guess = n_symbols_hint ? n_symbols_hint : (256ull << 20);
+    c->pool.hint(guess * 18 + (320ull << 20));
+    g.cap_words = text_words(guess) + 2;
+    if (dalloc(c->pool, &c->d_packed, g.cap_words) || dalloc(c->pool, &c->d_packed_err, 4) ||
+        dalloc(c->pool, &g.d_stage[0], kStageBytes + 64) || dalloc(c->pool, &g.d_stage[1], kStageBytes + 64))
+        return -1;
+    CUDA_TRY(cudaMemsetAsync(c->d_packed_err, 0, 16, c->st));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->st));
+    g.cur = 0; g.fill = 0; g.n = 0;
+    g.active = true;
+    return 0;
+}
+
+int debwt_ingest_reserve(debwt_ctx* c, char** buf, uint64_t* cap) {
+    if (!c || !buf || !cap) FAIL("null argument");
+    auto& g = c->ing;
+    if (!g.active) FAIL("no streaming input open: call debwt_ingest_begin first");
+    if (bind_device(c->device)) return -1;
+    if (g.fill + 4096 > kStageBytes && ingest_flush(c, false)) return -1;      // nearly full: ship it
+    if (g.busy[g.cur]) { CUDA_TRY(cudaEventSynchronize(g.done[g.cur])); g.busy[g.cur] = false; }
+    *buf = reinterpret_cast<char*>(g.h_stage[g.cur] + g.fill);
+    *cap = kStageBytes - g.fill;
+    return 0;
+}
+
+int debwt_ingest_commit(debwt_ctx* c, uint64_t n_written) {
+    if (!c) FAIL("null context");
+    auto& g = c->ing;
+    if (!g.active) FAIL("no streaming input open: call debwt_ingest_begin first");
+    if (g.fill + n_written > kStageBytes) FAIL("debwt_ingest_commit: more bytes than were reserved");
+    if (bind_device(c->device)) return -1;
+    g.fill += n_written;
+    if (g.fill + 4096 > kStageBytes) return ingest_flush(c, false);
+    return 0;
+}
+
+int debwt_ingest_append(debwt_ctx* c, const char* chunk, uint64_t n) {
+    while (n) {
+        char* buf = nullptr;
+        uint64_t cap = 0;
+        if (debwt_ingest_reserve(c, &buf, &cap)) return -1;
+        const u64 m = n < cap ? n : cap;
+        memcpy(buf, chunk, m);
+        if (debwt_ingest_commit(c, m)) return -1;
+        chunk += m;
+        n -= m;
+    }
+    return 0;
+}
+
+int debwt_ingest_end(debwt_ctx* c, const uint64_t* seps, uint64_t n_records) {
+    if (!c || !seps) FAIL("null argument");
+    auto& g = c->ing;
+    if (!g.active) FAIL("no streaming input open: call debwt_ingest_begin first");
+    if (bind_device(c->device)) return -1;
+    if (g.busy[g.cur]) { CUDA_TRY(cudaEventSynchronize(g.done[g.cur])); g.busy[g.cur] = false; }
+    if (ingest_flush(c, true)) return -1;
+    g.active = false;
+    const u64 n = g.n;
+    if (check_seps(seps, n_records, n)) { c->d_packed = nullptr; return -1; }
+    c->seps.assign(seps, seps + n_records);
+    c->n = n; c->n_rec = n_records;
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->st));
+    CUDA_TRY(cudaStreamSynchronize(c->st));
+    CUDA_TRY(cudaEventElapsedTime(&c->stats.ms_h2d, c->ev[0], c->ev[1]));
+    c->input_mark = c->pool.mark();
     return 0;
 }
 

@@ -89,6 +89,20 @@ struct debwt_ctx {
     std::vector<u64> seps;
     u8* d_ascii = nullptr;         // owned unless external
     const u8* d_ascii_ext = nullptr;
+    // streaming ingest (debwt_ingest_*): the text arrives in chunks through pinned staging and is packed on the fly
+    struct Ingest {
+        bool active = false;
+        u8* h_stage[2] = {nullptr, nullptr};       // pinned host staging (owned by the context, allocated once)
+        u8* d_stage[2] = {nullptr, nullptr};       // device staging (arena)
+        cudaEvent_t done[2] = {nullptr, nullptr};  // stage i's copy + pack have run
+        bool busy[2] = {false, false};
+        int cur = 0;
+        u64 fill = 0;                              // bytes in the current stage (incl. the < 32 carried over)
+        u64 n = 0;                                 // symbols packed so far (a multiple of 32 until the end)
+        u64 cap_words = 0;
+    } ing;
+    u64* d_packed = nullptr;          // packed text produced by the ingest (skips K1 in the build)
+    u32* d_packed_err = nullptr;
     // result
     u64* d_bwt = nullptr;
     u64* d_sharp = nullptr;

@@ -56,6 +56,11 @@ int debwt_dev_extract(const void* d_words, uint64_t pos_lo, uint64_t pos_hi, con
     return k_extract_range(P64(d_words), pos_lo, pos_hi, P64(d_seps), n_rec, idx_base, P64(d_keys), S(stream));
 }
 
+int debwt_dev_extract_slice(const void* d_words, uint64_t n_symbols, uint64_t pos_lo, uint64_t pos_hi, const void* d_seps,
+                            uint64_t n_rec, uint64_t idx_base, void* d_keys, void* stream) {
+    return k_extract_slice(P64(d_words), n_symbols, pos_lo, pos_hi, P64(d_seps), n_rec, idx_base, P64(d_keys), S(stream));
+}
+
 uint64_t debwt_dev_sort_workspace_bytes(uint64_t n, int cfg) { return sort_workspace_bytes(n, cfg); }
 uint64_t debwt_dev_branch_workspace_bytes(uint64_t n) { return branch_workspace_bytes(n) + 64; }
 uint64_t debwt_dev_scan_workspace_bytes(uint64_t n_words) { return scan_workspace_bytes(n_words) + 64; }

@@ -207,8 +207,13 @@ __global__ void __launch_bounds__(TPB) partition_scatter_p2p_kernel(const u64* _
 // consecutive items of one destination's run, so every peer store of a warp is one contiguous 256-byte run instead of
 // G short ones (a 32-64 byte store per destination and warp row reached only a fifth of the NVLink bandwidth on the
 // 3.1 Gbp build; profiles/r01_c3_3p1gbp_8gpu.log).
+// Blocks visit the tiles in a strided order (tile = block * stride mod grid, stride coprime with the grid): when the
+// input is sorted -- the in-edge queries are -- consecutive tiles all go to the same owner, every rank walks the owners
+// in the same order, and all ranks would store into ONE rank's memory at a time (incast on a single NVLink port: the
+// query exchange took twice as long as the key exchange for the same volume, profiles/r02_c3_8gpu_phases.md).
 __global__ void __launch_bounds__(TPB) partition_scatter_p2p_staged_kernel(const u64* __restrict__ a, OwnerFn owner, u64 n,
-                                                                          u32 n_ranks, u64* __restrict__ cursors, PeerDst dst) {
+                                                                          u32 n_ranks, u64* __restrict__ cursors, PeerDst dst,
+                                                                          u32 stride) {
     constexpr int NW = TPB / 32;
     __shared__ u32 s_wcnt[NW][MAX_RANKS];
     __shared__ u64 s_base[MAX_RANKS];
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(TPB) partition_scatter_p2p_staged_kernel(const
     __shared__ u64 s_items[PART_TILE];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = lanemask_lt();
-    const u64 base = (u64)blockIdx.x * PART_TILE;
+    const u64 base = (((u64)blockIdx.x * stride) % gridDim.x) * PART_TILE;
     u8 dd[PART_ITEMS];
     u64 vv[PART_ITEMS];
     u32 mine = 0;
@@ -531,7 +536,14 @@ int k_partition_scatter_p2p(const u64* a, const PartitionBy& by, u64 n, u32 n_ra
     for (u32 r = 0; r < MAX_RANKS; ++r) pd.ptr[r] = r < n_ranks ? dst[r] : nullptr;
     static const bool direct = getenv("DEBWT_P2P_DIRECT") != nullptr;      // the unstaged variant, kept for comparison
     if (direct) partition_scatter_p2p_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd);
-    else partition_scatter_p2p_staged_kernel<<<grid_for(n, PART_TILE), TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd);
+    else {
+        const unsigned grid = grid_for(n, PART_TILE);
+        auto gcd = [](unsigned x, unsigned y) { while (y) { const unsigned t = x % y; x = y; y = t; } return x; };
+        unsigned stride = (unsigned)(grid * 0.6180339887) | 1u;            // golden-ratio stride: neighbours in time are far apart in the input
+        while (stride > 1 && gcd(stride, grid) != 1) stride -= 2;
+        if (grid < 8) stride = 1;
+        partition_scatter_p2p_staged_kernel<<<grid, TPB, 0, st>>>(a, make_owner(by), n, n_ranks, d_cursors, pd, stride);
+    }
     LAUNCHED(1);
 }
 

@@ -24,37 +24,9 @@ namespace {
 
 using namespace radix;
 
-// ---- async proxy (bulk copy engine) and mbarrier helpers -------------------------------------
+// ---- async proxy (bulk copy engine) helpers -------------------------------------
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-    const u32 a = smem_u32(bar);
-    u32 done;
-    u32 spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (!done && ++spins > (1u << 22)) __trap();              // never hang the device on a bug
-    } while (!done);
-}
-// global -> shared, completes `bytes` on the mbarrier
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, u32 bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 // shared -> global, tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, u32 bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
@@ -62,7 +34,6 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, u32
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int THREADS, int ITEMS>
 struct BulkSmem {

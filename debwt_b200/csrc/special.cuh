@@ -29,6 +29,27 @@ __host__ __device__ inline bool special_less(const u64* __restrict__ words, cons
     }
 }
 
+// The same with the records of both positions known (suffix t = rec * 32 + j starts at seps[rec] - j): no record search.
+__host__ __device__ inline bool special_less_rec(const u64* __restrict__ words, const u64* __restrict__ seps, u64 R,
+                                                 u64 pa, u64 ra, u64 pb, u64 rb) {
+    if (pa == pb) return false;
+    for (;;) {
+        const u64 da = seps[ra] - pa, db = seps[rb] - pb;
+        const u64 m = da < db ? da : db;
+        for (u64 off = 0; off < m; off += 32) {
+            u64 wa = text_window32(words, pa + off), wb = text_window32(words, pb + off);
+            const u64 len = m - off;
+            if (len < 32) { const u64 mask = ~(~0ull >> (2 * len)); wa &= mask; wb &= mask; }
+            if (wa != wb) return wa < wb;
+        }
+        if (da != db) return da > db;
+        const bool a_end = (ra + 1 == R), b_end = (rb + 1 == R);
+        if (a_end || b_end) return !a_end && b_end;
+        pa = seps[ra] + 1; pb = seps[rb] + 1;
+        ++ra; ++rb;
+    }
+}
+
 // what the host needs to know about one special suffix (position = seps[rec] - j)
 struct SpecialInfo {
     u64 w0;        // 32 symbols starting at the position
@@ -40,8 +61,12 @@ struct SpecialInfo {
     u8 pad_[2];
 };
 
-// one block per special suffix t = rec*32 + j: rank by counting against all others + window gather +
-// insertion point.  m = 32 R.
+// Ranks the m = 32 R special suffixes (suffix t = rec*32 + j) under special_less and gathers their windows and
+// insertion points.  Up to kSpecialAllPairs suffixes: one block per suffix counts the smaller ones (one launch).
+// Beyond: a bitonic sorting network over the suffix ids with the same comparator -- O(m log^2 m) comparisons, every
+// stage fully parallel, the text never leaves the device (the reference sorts them with a single-threaded qsort,
+// src/collect#$.c:157).
+constexpr u64 kSpecialAllPairs = 16384;
 int k_special_scan(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n_keys, KeyIndex ki,
                    SpecialInfo* out, cudaStream_t st);
 

@@ -183,18 +183,19 @@ __device__ __forceinline__ u64 tile_window(const TileText& t, u32 local) {      
     return sft ? (a << sft) | (t.w[i + 1] >> (64 - sft)) : a;
 }
 
+// positions [pos_lo, pos_hi) of the text (pos_lo a multiple of 32); key index = p - 32 r - idx_base
 __global__ void __launch_bounds__(TPB) extract_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                      const u64* __restrict__ seps, u64 n_rec,
-                                                     u64* __restrict__ keys) {
+                                                     u64* __restrict__ keys, u64 pos_lo, u64 pos_hi, u64 idx_base) {
     __shared__ TileText t;
-    const u64 base = (u64)blockIdx.x * TILE_POS;
+    const u64 base = pos_lo + (u64)blockIdx.x * TILE_POS;
     tile_load(t, words, nwords_total, base, n, seps, n_rec);
     const bool one_record = t.rec_first == t.rec_last;
 #pragma unroll
     for (int j = 0; j < TILE_ROWS; ++j) {
         const u32 local = j * TPB + threadIdx.x;
         const u64 p = base + local;
-        if (p >= n) continue;
+        if (p >= pos_hi) continue;
         u64 r = t.rec_first, sep = t.sep_first;
         if (!one_record) {
             r = record_of(seps, n_rec, p);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(TPB) extract_kernel(const u64* __restrict__ wo
             sep = seps[r];
         }
         if (p + KMER > sep) continue;              // window would contain the separator
-        st_stream(keys + (p - (u64)KMER * r), tile_window(t, local));
+        st_stream(keys + (p - (u64)KMER * r - idx_base), tile_window(t, local));
     }
 }
 
@@ -263,7 +264,14 @@ int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cud
 }
 
 int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st) {
-    extract_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, keys);
+    return k_extract_slice(words, n, 0, n, d_seps, n_rec, 0, keys, st);
+}
+
+int k_extract_slice(const u64* words, u64 n, u64 pos_lo, u64 pos_hi, const u64* d_seps, u64 n_rec, u64 idx_base, u64* keys,
+                    cudaStream_t st) {
+    if (pos_hi <= pos_lo) return 0;
+    extract_kernel<<<grid_for(pos_hi - pos_lo, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, keys, pos_lo, pos_hi,
+                                                                        idx_base);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -696,11 +704,81 @@ __global__ void __launch_bounds__(128) special_scan_kernel(const u64* __restrict
 }
 }  // namespace
 
+namespace {
+constexpr u32 SPEC_INF = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(TPB) special_ids_kernel(u32* __restrict__ ids, u64 m, u64 mp2) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i < mp2) ids[i] = i < m ? (u32)i : SPEC_INF;
+}
+
+__device__ __forceinline__ bool special_id_less(u32 x, u32 y, const u64* __restrict__ words, const u64* __restrict__ seps,
+                                                u64 n_rec) {
+    if (x == SPEC_INF) return false;                 // padding ids are larger than every suffix
+    if (y == SPEC_INF) return true;
+    return special_less_rec(words, seps, n_rec, seps[x >> 5] - (x & 31), x >> 5, seps[y >> 5] - (y & 31), y >> 5);
+}
+
+// one compare-exchange stage of the bitonic network (partner distance j inside runs of length k)
+__global__ void __launch_bounds__(TPB) special_bitonic_kernel(u32* __restrict__ ids, u64 mp2, u64 j, u64 k,
+                                                             const u64* __restrict__ words, const u64* __restrict__ seps, u64 n_rec) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i >= mp2) return;
+    const u64 l = i ^ j;
+    if (l <= i) return;
+    const u32 a = ids[i], b = ids[l];
+    const bool ascending = (i & k) == 0;
+    const bool swap = ascending ? special_id_less(b, a, words, seps, n_rec) : special_id_less(a, b, words, seps, n_rec);
+    if (swap) { ids[i] = b; ids[l] = a; }
+}
+
+// windows, neighbours and insertion point of the suffix that ended up at sorted position `pos`
+__global__ void __launch_bounds__(TPB) special_info_kernel(const u32* __restrict__ ids, u64 m, const u64* __restrict__ words,
+                                                          const u64* __restrict__ seps, const u64* __restrict__ k, u64 n_keys,
+                                                          KeyIndex ki, SpecialInfo* __restrict__ out) {
+    const u64 pos = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (pos >= m) return;
+    const u32 a = ids[pos];
+    const u64 pa = seps[a >> 5] - (a & 31);
+    const u32 j = a & 31;
+    SpecialInfo o;
+    o.w0 = text_window32(words, pa);
+    o.w1 = text_window32(words, pa + j + 1);
+    o.rank = (u32)pos;
+    o.prev = (u8)text_symbol(words, pa - 1);
+    o.next = (u8)text_symbol(words, pa + 31);
+    o.pad_[0] = o.pad_[1] = 0;
+    o.ins = j ? indexed_upper_bound(k, ki, (o.w0 & ~(~0ull >> (2 * j))) | (~0ull >> (2 * j))) : n_keys;
+    out[a] = o;
+}
+}  // namespace
+
 int k_special_scan(const u64* words, const u64* d_seps, u64 n_rec, const u64* sorted, u64 n_keys, KeyIndex ki,
                    SpecialInfo* out, cudaStream_t st) {
-    special_scan_kernel<<<(unsigned)(n_rec * 32), 128, 0, st>>>(words, d_seps, n_rec, sorted, n_keys, ki, out);
-    DEBWT_COUNT(1);
-    CUDA_TRY(cudaGetLastError());
+    const u64 m = n_rec * 32;
+    if (m <= kSpecialAllPairs) {
+        special_scan_kernel<<<(unsigned)m, 128, 0, st>>>(words, d_seps, n_rec, sorted, n_keys, ki, out);
+        DEBWT_COUNT(1);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (m >= SPEC_INF) { set_error("too many records for the sentinel-window sort (32 R must be below 2^32)"); return -1; }
+    u64 mp2 = 1;
+    while (mp2 < m) mp2 <<= 1;
+    u32* ids = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ids), mp2 * 4, st));
+    special_ids_kernel<<<grid_for(mp2, TPB), TPB, 0, st>>>(ids, m, mp2);
+    unsigned launches = 1;
+    for (u64 k = 2; k <= mp2; k <<= 1)
+        for (u64 j = k >> 1; j > 0; j >>= 1) {
+            special_bitonic_kernel<<<grid_for(mp2, TPB), TPB, 0, st>>>(ids, mp2, j, k, words, d_seps, n_rec);
+            ++launches;
+        }
+    special_info_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(ids, m, words, d_seps, sorted, n_keys, ki, out);
+    DEBWT_COUNT(launches + 1);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ids, st);
+    if (e != cudaSuccess) { set_error(std::string("sentinel-window sort: ") + cudaGetErrorString(e)); return -1; }
     return 0;
 }
 

@@ -15,6 +15,9 @@ int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st);
 inline u64 text_words(u64 n) { return (n + 32 + 31) / 32 + 1; }
 // all in-record 32-mers; key index of window p in record r is p - 32 r.  keys: n - 32 R entries.
 int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st);
+// the same for the positions [pos_lo, pos_hi) only (pos_lo a multiple of 32); key index = p - 32 r - idx_base
+int k_extract_slice(const u64* words, u64 n, u64 pos_lo, u64 pos_hi, const u64* d_seps, u64 n_rec, u64 idx_base, u64* keys,
+                    cudaStream_t st);
 
 // [8][256] digit counts of the keys k_extract writes, computed from the packed text (see stages.cu); applies when the
 // per-record corrections are negligible next to the sweep.

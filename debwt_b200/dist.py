@@ -115,6 +115,18 @@ class Comm:
             t.copy_(h)
         return t
 
+    def gather_to0(self, t: torch.Tensor):
+        """rank 0 gets the list of every rank's `t` (same length everywhere); others get None"""
+        if self.size == 1:
+            return [t]
+        src = self._h(t.contiguous())
+        outs = [torch.empty_like(src) for _ in range(self.size)] if self.rank == 0 else None
+        self.dist.gather(src, outs, dst=0, group=self.group)
+        if self.rank != 0:
+            self.bytes_sent += src.numel() * src.element_size()
+            return None
+        return [o.to(t.device) for o in outs]
+
     def all_to_all_v(self, t: torch.Tensor, send_counts) -> tuple[torch.Tensor, list[int]]:
         """`t` is grouped by destination rank with `send_counts[r]` items for rank r"""
         send_counts = [int(c) for c in send_counts]
@@ -200,9 +212,13 @@ class CudaOps:
     def pack(self, ascii_slice, n_valid, words_out, nwords, err):
         self._ck(self.L.debwt_dev_pack(_p(ascii_slice), _u64(n_valid), _p(words_out), _u64(nwords), _p(err), self._st()))
 
-    def extract(self, words, pos_lo, pos_hi, seps, n_rec, idx_base, keys_out):
-        self._ck(self.L.debwt_dev_extract(_p(words), _u64(pos_lo), _u64(pos_hi), _p(seps), _u64(n_rec), _u64(idx_base),
-                                          _p(keys_out), self._st()))
+    def extract(self, words, pos_lo, pos_hi, seps, n_rec, idx_base, keys_out, n_symbols=None):
+        if n_symbols is None:
+            self._ck(self.L.debwt_dev_extract(_p(words), _u64(pos_lo), _u64(pos_hi), _p(seps), _u64(n_rec), _u64(idx_base),
+                                              _p(keys_out), self._st()))
+        else:
+            self._ck(self.L.debwt_dev_extract_slice(_p(words), _u64(n_symbols), _u64(pos_lo), _u64(pos_hi), _p(seps), _u64(n_rec),
+                                                    _u64(idx_base), _p(keys_out), self._st()))
 
     def sort(self, keys, timed: bool = False):
         n = keys.numel()
@@ -366,6 +382,11 @@ class CudaOps:
         self._ck(self.L.debwt_dev_sort_blue(_p(blue), _p(bt["kmer"]), _p(bt["blue"]), _u64(bt["B"]), _u64(bt["M"]), _p(codes),
                                             _p(sep), _u64(dollar_index), _u64(n_codes), _p(work), self._st()))
 
+    def bwt_segment(self, word_lo, word_hi):
+        """zeroed words [word_lo, word_hi) of the BWT: (the segment, a handle the emit kernels index with GLOBAL word numbers)"""
+        seg = self.zeros(max(word_hi - word_lo, 0) + 1)
+        return seg, _Shifted(seg, 8 * word_lo)
+
     def fill_range(self, gmask, n_keys, key_base, n_symbols, spec_rows, word_lo, word_hi, bwt):
         self._ck(self.L.debwt_dev_fill_range(_p(gmask), _u64(n_keys), _u64(key_base), _u64(n_symbols), _p(spec_rows),
                                              _u64(spec_rows.numel()), _u64(word_lo), _u64(word_hi), _p(bwt), self._st()))
@@ -412,6 +433,16 @@ def special_tables_host(info_np, ins_by_t, seps_np, n_rec):
 # --------------------------------------------------------------------------------------------------
 # fused bucket + exchange over NVLink peer memory
 # --------------------------------------------------------------------------------------------------
+class _Shifted:
+    """a device buffer addressed from a virtual origin `shift` bytes before its first element"""
+
+    def __init__(self, t: torch.Tensor, shift: int):
+        self.t, self.shift = t, shift
+
+    def data_ptr(self):
+        return self.t.data_ptr() - self.shift
+
+
 class _RawCuda:
     """zero-copy view of a raw device pointer for torch.as_tensor"""
 
@@ -574,7 +605,7 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     cnt = valid_windows_before(pos_hi, seps) - idx_base if n_valid else 0
     keys = ops.empty(cnt)
     if cnt:
-        ops.extract(words, pos_lo, pos_hi, d_seps, R, idx_base, keys)
+        ops.extract(words, pos_lo, pos_hi, d_seps, R, idx_base, keys, n_symbols=N)
     sample = torch.full((SAMPLES_PER_RANK,), I64_ALL_ONES, dtype=torch.int64, device=keys.device)
     ns = min(cnt, SAMPLES_PER_RANK)
     if ns:
@@ -680,18 +711,37 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     ops.sort_blue(blue, bt, codes, sep, dollar_index, s_tot)
 
     tick('blue')
-    # 8. every rank emits its own run of BWT rows; segments are summed (disjoint bits) onto rank 0
+    # 8. every rank emits its own contiguous run of BWT rows into a buffer of just that size.
+    #    Rank r owns the rows from its first key's row up to the next rank's first key's row; the sentinel-window suffixes
+    #    inserted in between belong to the rank whose keys precede them.  Rank 0 stitches: interior words are copied,
+    #    the at most one word shared with a neighbour is OR-ed (disjoint 2-bit fields).
     n_out = (N + 31) // 32
-    bwt = ops.zeros(n_out + 1)
-    if n_loc:
-        row_first = key_base + int(np.searchsorted(ins, np.uint64(key_base), side="right"))
-        g_last = key_base + n_loc - 1
-        row_last = g_last + int(np.searchsorted(ins, np.uint64(g_last), side="right"))
-        ops.fill_range(gmask, n_loc, key_base, N, d_rows, row_first >> 5, (row_last >> 5) + 1, bwt)
-    sharp, dollar = ops.emit_blue(blue, bt, key_base, d_ins, bwt, R)
+    kb = np.concatenate(([0], np.cumsum(n_all))).astype(np.uint64)
+
+    def row_lo(q):
+        return 0 if int(kb[q]) == 0 else int(kb[q]) + int(np.searchsorted(ins, kb[q], side="right"))
+    r_lo_all = [row_lo(q) for q in range(G)] + [N]
+    my_lo, my_hi = r_lo_all[r], r_lo_all[r + 1]
+    w_lo, w_hi = my_lo >> 5, (my_hi + 31) >> 5
+    seg, bwt_h = ops.bwt_segment(w_lo, w_hi)
+    if my_hi > my_lo:
+        if n_loc:
+            ops.fill_range(gmask, n_loc, key_base, N, d_rows, w_lo, w_hi, bwt_h)
+        t_lo, t_hi = int(np.searchsorted(rows, np.uint64(my_lo), side="left")), int(np.searchsorted(rows, np.uint64(my_hi), side="left"))
+        if t_hi > t_lo:
+            ops.emit_special(d_rows[t_lo:t_hi], d_chr[t_lo:t_hi], bwt_h)
+    sharp, dollar = ops.emit_blue(blue, bt, key_base, d_ins, bwt_h, R)
+    seg_words = [((r_lo_all[q + 1] + 31) >> 5) - (r_lo_all[q] >> 5) for q in range(G)]
+    mx = max(max(seg_words), 1)
+    pad = seg if seg.numel() == mx else torch.cat([seg[:min(seg.numel(), mx)], seg.new_zeros(max(mx - seg.numel(), 0))])
+    parts = comm.gather_to0(pad[:mx].contiguous())
+    bwt = None
     if r == 0:
-        ops.emit_special(d_rows, d_chr, bwt)
-    comm.reduce_sum_to0(bwt)
+        bwt = ops.zeros(n_out + 1)
+        for q in range(G):
+            if seg_words[q] > 0:
+                lo_q = r_lo_all[q] >> 5
+                bwt[lo_q:lo_q + seg_words[q]] |= parts[q][:seg_words[q]]
     sharp_all, _ = comm.all_gather_var(sharp)
     comm.all_reduce_max(dollar)
     tick('emit+reduce')

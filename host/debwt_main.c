@@ -11,11 +11,18 @@
  *   <out>.$  row holding '$'
  * Differences: -j is accepted and ignored (Jellyfish is replaced by on-GPU count-by-sort), -t is
  * accepted and ignored (the work runs on the GPU), -g picks the CUDA device, no temp files.
- * All computation happens in libdebwt_b200.so (include/debwt_b200.h); there is no CPU fallback.
+ *
+ * The reference reads the input twice through kseq (src/collect#$.c:37-48, 66-86) before anything else starts.  Here the
+ * file is read ONCE and streamed: the reader writes the bases straight into the library's pinned staging window
+ * (debwt_ingest_reserve / _commit), every full window is copied to the GPU and 2-bit packed while the next one is being
+ * parsed, and the CUDA context is created on a second thread while the first megabytes are read.  The result comes back
+ * into page-locked memory.  All computation happens in libdebwt_b200.so (include/debwt_b200.h); there is no CPU fallback.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
 
 #include "../include/debwt_b200.h"
@@ -48,6 +55,69 @@ static int write_file(const char* path, const void* data, size_t bytes) {
     return 0;
 }
 
+/* ---- context creation on a second thread (CUDA start-up overlaps the first reads) ---- */
+typedef struct { int gpu; debwt_ctx* ctx; int rc; char err[256]; } create_job;
+static void* create_thread(void* p) {
+    create_job* j = (create_job*)p;
+    j->rc = debwt_create(&j->ctx, j->gpu);
+    if (j->rc) { strncpy(j->err, debwt_last_error(), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }
+    return NULL;
+}
+
+/* ---- sink of the streaming reader: T = S1 # S2 # ... Sn $ written into the library's staging window ---- */
+typedef struct {
+    debwt_ctx* ctx;
+    char* win;                 /* current window */
+    uint64_t cap, used;        /* its capacity / bytes written and not yet committed */
+    uint64_t n;                /* symbols of T emitted so far */
+    uint64_t* seps;
+    uint64_t nrec, sep_cap;
+    int pending_sep;           /* the separator after the last record is written once we know whether it is '#' or '$' */
+    int failed;
+} sink_t;
+
+static int sink_room(sink_t* s) {
+    if (s->used && debwt_ingest_commit(s->ctx, s->used)) return -1;
+    s->used = 0;
+    if (debwt_ingest_reserve(s->ctx, &s->win, &s->cap)) return -1;
+    return 0;
+}
+
+static int sink_put(sink_t* s, const unsigned char* p, uint64_t n) {
+    if (!s->ctx) { s->n += n; return 0; }           /* dry run (no device): only the input checks */
+    while (n) {
+        if (s->used == s->cap && sink_room(s)) { s->failed = 1; return 2; }
+        uint64_t m = s->cap - s->used;
+        if (m > n) m = n;
+        memcpy(s->win + s->used, p, m);
+        s->used += m; s->n += m; p += m; n -= m;
+    }
+    return 0;
+}
+
+static int on_bases(void* u, const unsigned char* p, uint64_t n) {
+    sink_t* s = (sink_t*)u;
+    if (s->pending_sep) {
+        const unsigned char c = '#';
+        s->pending_sep = 0;
+        if (sink_put(s, &c, 1)) return 2;
+    }
+    return sink_put(s, p, n);
+}
+
+static int on_record(void* u, uint64_t len) {
+    sink_t* s = (sink_t*)u;
+    if (len <= 32) { fprintf(stderr, "Length <= 32!\n"); return 3; }                  /* src/collect#$.c:41-45 */
+    if (s->nrec == s->sep_cap) {
+        s->sep_cap = s->sep_cap ? s->sep_cap * 2 : 64;
+        s->seps = (uint64_t*)realloc(s->seps, s->sep_cap * 8);
+        if (!s->seps) { fprintf(stderr, "out of host memory\n"); return 3; }
+    }
+    s->seps[s->nrec++] = s->n;             /* position the separator will take */
+    s->pending_sep = 1;
+    return 0;
+}
+
 int main(int argc, char* argv[]) {
     if (argc < 4 || (argc & 1) == 1) { usage(); return 1; }
     const char* source = argv[argc - 1];
@@ -71,43 +141,61 @@ int main(int argc, char* argv[]) {
     remove(obj);
 
     double t0 = now_s();
+    create_job job;
+    memset(&job, 0, sizeof job);
+    job.gpu = gpu;
+    pthread_t th;
+    if (pthread_create(&th, NULL, create_thread, &job) != 0) { fprintf(stderr, "cannot start a thread\n"); return 1; }
+
     fastx_t* fx = fastx_open(source);
     if (!fx) { fprintf(stderr, "can not open ref file\n"); return 1; }
-    /* T = S1 # S2 # ... Sn $ assembled in one host buffer (src/collect#$.c:56-90) */
-    char* text = NULL;
-    uint64_t n = 0, cap = 0, nrec = 0, sep_cap = 0;
-    uint64_t* seps = NULL;
-    int rc;
-    while ((rc = fastx_read(fx)) == 1) {
-        if (fx->len <= 32) { fprintf(stderr, "Length <= 32!\n"); return 1; }            /* src/collect#$.c:41-45 */
-        if (n + fx->len + 1 > cap) {
-            cap = cap ? cap : (1u << 20);
-            while (cap < n + fx->len + 1) cap += cap >> 1;
-            text = (char*)realloc(text, cap);
-            if (!text) { fprintf(stderr, "out of host memory\n"); return 1; }
-        }
-        memcpy(text + n, fx->seq, fx->len);
-        n += fx->len;
-        if (nrec == sep_cap) { sep_cap = sep_cap ? sep_cap * 2 : 64; seps = (uint64_t*)realloc(seps, sep_cap * 8); }
-        seps[nrec++] = n;
-        text[n++] = '#';
+    /* an upper bound of N for a plain file is its size; a gzip file (magic 1f 8b) gives none */
+    uint64_t hint = 0;
+    {
+        struct stat sb;
+        FILE* f = fopen(source, "rb");
+        unsigned char magic[2] = {0, 0};
+        if (f) { if (fread(magic, 1, 2, f) != 2) magic[0] = 0; fclose(f); }
+        if (stat(source, &sb) == 0 && !(magic[0] == 0x1f && magic[1] == 0x8b)) hint = (uint64_t)sb.st_size + 64;
     }
-    fastx_close(fx);
-    if (rc < 0) { fprintf(stderr, "malformed input file\n"); return 1; }
-    if (nrec == 0) { fprintf(stderr, "no sequence found in %s\n", source); return 1; }
-    text[n - 1] = '$';
-    double t1 = now_s();
-    fprintf(stderr, "BWTLEN=%llu (%llu records), read in %.3f s\n", (unsigned long long)n, (unsigned long long)nrec, t1 - t0);
-
-    debwt_ctx* ctx = NULL;
-    if (debwt_create(&ctx, gpu) || debwt_set_text(ctx, text, n, seps, nrec) || debwt_build(ctx, k)) {
-        fprintf(stderr, "deBWT: %s\n", debwt_last_error());
+    pthread_join(th, NULL);
+    if (job.rc) {
+        /* no usable device: still report what is wrong with the input first, like the reference's first pass does */
+        sink_t dry;
+        memset(&dry, 0, sizeof dry);
+        int drc = fastx_stream(fx, on_bases, on_record, &dry);
+        if (drc < 0) fprintf(stderr, "malformed input file\n");
+        else if (drc == 0 && dry.nrec == 0) fprintf(stderr, "no sequence found in %s\n", source);
+        if (drc == 0 && dry.nrec) fprintf(stderr, "deBWT: %s\n", job.err);
         return 1;
     }
-    free(text);
+    debwt_ctx* ctx = job.ctx;
+    double t_ctx = now_s();
+    if (debwt_ingest_begin(ctx, hint)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+
+    sink_t s;
+    memset(&s, 0, sizeof s);
+    s.ctx = ctx;
+    int rc = fastx_stream(fx, on_bases, on_record, &s);
+    fastx_close(fx);
+    if (rc == 2 || s.failed) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+    if (rc == 3) return 1;
+    if (rc < 0) { fprintf(stderr, "malformed input file\n"); return 1; }
+    if (s.nrec == 0) { fprintf(stderr, "no sequence found in %s\n", source); return 1; }
+    {
+        const unsigned char c = '$';                       /* the last separator is '$' (src/collect#$.c:83) */
+        if (sink_put(&s, &c, 1)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+    }
+    if (s.used && debwt_ingest_commit(ctx, s.used)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+    if (debwt_ingest_end(ctx, s.seps, s.nrec)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+    double t1 = now_s();
+    fprintf(stderr, "BWTLEN=%llu (%llu records), context %.3f s, read + parse + upload + pack %.3f s\n", (unsigned long long)s.n,
+            (unsigned long long)s.nrec, t_ctx - t0, t1 - t_ctx);
+
+    if (debwt_build(ctx, k)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
     uint64_t nsym = 0, nwords = 0, nsharp = 0, dollar = 0;
     if (debwt_result_sizes(ctx, &nsym, &nwords, &nsharp)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
-    uint64_t* bwt = (uint64_t*)malloc((nwords ? nwords : 1) * 8);
+    uint64_t* bwt = (uint64_t*)debwt_host_alloc((nwords ? nwords : 1) * 8);     /* page-locked: the D2H copy runs at link speed */
     uint64_t* sharp = (uint64_t*)malloc((nsharp ? nsharp : 1) * 8);
     if (!bwt || !sharp) { fprintf(stderr, "out of host memory\n"); return 1; }
     if (debwt_result_copy(ctx, bwt, sharp, &dollar)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
@@ -125,9 +213,10 @@ int main(int argc, char* argv[]) {
     p2[ol + 1] = '$';
     if (write_file(p2, &dollar, 8)) return 1;
     double t3 = now_s();
-    fprintf(stderr, "GPU build %.3f s (device %.1f ms: sort %.1f ms, %u launches), write %.3f s; branch k-mers %llu, blue %llu, SP codes %llu\n",
+    fprintf(stderr, "GPU build + download %.3f s (device %.1f ms: sort %.1f ms, %u launches), write %.3f s; branch k-mers %llu, blue %llu, SP codes %llu\n",
             t2 - t1, st.ms_total, st.ms_sort, st.total_launches, t3 - t2, (unsigned long long)st.n_branch,
             (unsigned long long)st.n_blue, (unsigned long long)st.n_codes);
+    debwt_host_free(bwt);
     debwt_destroy(ctx);
     return 0;
 }

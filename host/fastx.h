@@ -24,7 +24,7 @@ typedef struct {
     uint64_t len, cap;
 } fastx_t;
 
-#define FASTX_BUF (1 << 20)
+#define FASTX_BUF (1 << 22)
 
 static inline fastx_t* fastx_open(const char* path) {
     gzFile fp = gzopen(path, "r");
@@ -113,6 +113,54 @@ static inline int fastx_read(fastx_t* f) {
         fastx_skip_line(f);
     }
     return 1;
+}
+
+/* Streaming variant: the bases of every record are handed to `bases` piece by piece (no per-record buffer, no second
+   copy), `record_end` is called after the last piece of a record with the record's length.  Either callback stops
+   the stream by returning non-zero.  Returns 0 at end of file, -1 on a malformed file, else the callback's value. */
+typedef int (*fastx_bases_fn)(void* user, const unsigned char* p, uint64_t n);
+typedef int (*fastx_record_fn)(void* user, uint64_t len);
+
+static inline int fastx_stream(fastx_t* f, fastx_bases_fn bases, fastx_record_fn record_end, void* user) {
+    int c, rc;
+    for (;;) {
+        if (f->last == 0) {
+            while ((c = fastx_getc(f)) >= 0 && c != '>' && c != '@') {}
+            if (c < 0) return 0;
+            f->last = c;
+        }
+        const int fastq = (f->last == '@');
+        f->last = 0;
+        uint64_t len = 0;
+        fastx_skip_line(f);                                  /* header */
+        for (;;) {                                           /* sequence lines */
+            c = fastx_getc(f);
+            if (c < 0) break;
+            if (c == '>' || (c == '@' && !fastq) || c == '+') { if (c != '+') f->last = c; break; }
+            if (c == '@' && fastq) { f->last = c; break; }
+            f->begin--;
+            for (;;) {
+                unsigned char* p = f->buf + f->begin;
+                unsigned char* nl = (unsigned char*)memchr(p, '\n', (size_t)(f->end - f->begin));
+                uint64_t n = nl ? (uint64_t)(nl - p) : (uint64_t)(f->end - f->begin);
+                uint64_t m = n;
+                while (m && (p[m - 1] == '\r' || p[m - 1] == ' ')) m--;
+                if (m && (rc = bases(user, p, m)) != 0) return rc;
+                len += m;
+                f->begin += (int)n + (nl ? 1 : 0);
+                if (nl) break;
+                if (fastx_getc(f) < 0) break;                /* refill */
+                f->begin--;
+            }
+        }
+        if (fastq && c == '+') {                             /* skip '+' line and the quality string */
+            fastx_skip_line(f);
+            uint64_t q = 0;
+            while (q < len && (c = fastx_getc(f)) >= 0) if (c != '\n' && c != '\r') q++;
+            fastx_skip_line(f);
+        }
+        if ((rc = record_end(user, len)) != 0) return rc;
+    }
 }
 
 #endif /* DEBWT_FASTX_H */

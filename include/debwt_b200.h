@@ -80,6 +80,23 @@ int debwt_set_text(debwt_ctx* ctx, const char* text, uint64_t n_symbols, const u
 int debwt_set_text_device(debwt_ctx* ctx, const void* d_text, uint64_t n_symbols, const uint64_t* seps,
                           uint64_t n_records);
 
+/* Streaming input: the text arrives in pieces while the file is still being read and decompressed.  The library keeps
+   two pinned staging buffers; the caller writes the next symbols of T (ASCII bases, '#' between records, '$' last)
+   straight into the window debwt_ingest_reserve() hands out and commits them; every full staging buffer is copied
+   to the device and 2-bit packed (K1) on the library's stream while the caller fills the other one, so file reading,
+   H2D and K1 overlap and the ASCII text is never resident on the device.  Replaces the TWO kseq passes of collect
+   (src/collect#$.c:37-48 and :66-86).  n_symbols_hint: an upper bound of N when known (plain file size), 0 otherwise. */
+int debwt_ingest_begin(debwt_ctx* ctx, uint64_t n_symbols_hint);
+int debwt_ingest_reserve(debwt_ctx* ctx, char** buf, uint64_t* capacity);
+int debwt_ingest_commit(debwt_ctx* ctx, uint64_t n_written);
+/* reserve + memcpy + commit for a caller that already holds a piece of T */
+int debwt_ingest_append(debwt_ctx* ctx, const char* chunk, uint64_t n);
+/* seps as in debwt_set_text; N is what was committed */
+int debwt_ingest_end(debwt_ctx* ctx, const uint64_t* seps, uint64_t n_records);
+/* page-locked host memory for the result / input buffers of a C host (no CUDA headers needed there) */
+void* debwt_host_alloc(uint64_t bytes);
+void debwt_host_free(void* p);
+
 /* ---- build: replaces mySort .. insertCase3, src/main.c:83-149 -------------------------------- */
 /* `k` is the CLI -k value (12..32).  The output does not depend on it; the
    device path always uses 32-base keys.  The result stays on the device until copied out. */

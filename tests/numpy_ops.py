@@ -87,7 +87,7 @@ class NumpyOps:
         sh = (U(2) * (U(31) - (np.arange(nwords * 32, dtype=np.uint64) & U(31))))
         u(words_out)[:nwords] = np.bitwise_or.reduce((code << sh).reshape(nwords, 32), axis=1)
 
-    def extract(self, words, pos_lo, pos_hi, seps, n_rec, idx_base, keys_out):
+    def extract(self, words, pos_lo, pos_hi, seps, n_rec, idx_base, keys_out, n_symbols=None):
         w, s = u(words), u(seps)
         p = np.arange(pos_lo, pos_hi, dtype=np.uint64)
         r = np.searchsorted(s, p, side="left")
@@ -338,6 +338,11 @@ class NumpyOps:
                 lo, hi = int(off[b]), int(off[b + 1])
                 seg = sorted(bl[lo:hi].tolist(), key=lambda e: sb[(e >> 4):])
                 bl[lo:hi] = seg
+
+    def bwt_segment(self, word_lo, word_hi):
+        """numpy restatement: the segment is a view into a full-size array, which is also the handle"""
+        full = torch.zeros(word_hi + 2, dtype=torch.int64)
+        return full[word_lo:word_hi + 1], full
 
     def fill_range(self, gmask, n_keys, key_base, n_symbols, spec_rows, word_lo, word_hi, bwt):
         g, rows, out = u(gmask), u(spec_rows), u(bwt)

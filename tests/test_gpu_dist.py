@@ -102,3 +102,51 @@ def test_sharded_multi_rank_one_gpu(world):
     for name, (ok, kl) in got.items():
         assert ok, name
         assert len(kl) == world and min(kl) >= 0
+
+
+# ---- the production exchange path: one process per GPU, NCCL + CUDA-IPC peer stores (needs >= 2 real GPUs) -----------
+def _worker_nccl(rank, world, port, names, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        comm = D.Comm()
+        assert not comm.staged and comm.coll_device.type == "cuda"
+        ops = D.CudaOps(rank)
+        for name in names:
+            recs = _case(name)
+            text, seps = api.join_records(recs)
+            stats = {}
+            w, s, d = D.build_sharded(text, seps, comm, ops, stats)
+            if rank == 0:
+                out.put((name, _check(recs, w, s, d), stats["keys_local"], D.PeerExchange._cache != {}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_nccl_p2p_real_gpus(world):
+    """partition_scatter_p2p*_kernel (peer stores over NVLink) + NCCL collectives on K9/K10-heavy inputs, against the oracle"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    names = ["c4_like_5x100k", "big_segments", "c3_like_600k_3rec", "c2_like_1m", "pathological", "survey_golden"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_nccl, args=(r, world, port, names, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=900)
+        assert p.exitcode == 0
+    got = {}
+    while not q.empty():
+        name, ok, kl, p2p = q.get()
+        got[name] = (ok, kl, p2p)
+    assert set(got) == set(names)
+    for name, (ok, kl, p2p) in got.items():
+        assert ok, name
+        assert p2p, "the peer-store exchange did not run"
+        assert len(kl) == world

@@ -6,7 +6,7 @@ import random
 import numpy as np
 import pytest
 
-from debwt_b200 import api, synth
+from debwt_b200 import api, binding, synth
 from debwt_b200.binding import DebwtError
 from oracle import coracle, stages as st
 from tests.util import as_bytes_records, golden, seeded_records, sha
@@ -266,3 +266,40 @@ def test_config2_full_size_lf_inversion():
     assert ok
     sym, _ = st.text_from_records(as_bytes_records(recs))
     assert (text == sym).all()
+
+
+# ---- f1: streaming ingest (debwt_ingest_*) -------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c4_like_5x100k", "c3_like_600k_3rec"])
+def test_streaming_ingest_equals_set_text(name):
+    recs = as_bytes_records(seeded_records(name))
+    text, seps = api.join_records(recs)
+    with api.BwtBuilder() as b:
+        b.set_text(text, seps)
+        b.build()
+        want = b.result()
+        for step in (1_000_003, 4097, 33):
+            if step < 1000 and text.size > 700_000:
+                continue
+            b.ingest((text[i:i + step] for i in range(0, text.size, step)), seps, n_hint=0 if step == 4097 else text.size)
+            b.build()
+            got = b.result()
+            assert all((x == y).all() for x, y in zip(want, got)), step
+            b.build()                                       # the packed input survives a build
+            assert all((x == y).all() for x, y in zip(want, b.result()))
+
+
+def test_streaming_ingest_large_and_errors():
+    # larger than one 32 MB staging window, hint far too small (the packed text is moved to a larger block)
+    recs = [synth.random_bases(21, 41_000_000), synth.random_bases(22, 30_000_001)]
+    text, seps = api.join_records(recs)
+    with api.BwtBuilder() as b:
+        b.ingest([text[:40_000_000], text[40_000_000:]], seps, n_hint=1_000_000)
+        b.build()
+        assert b.verify(text)[0] == 0
+        bad = text.copy()
+        bad[12345] = ord("N")
+        b.ingest([bad], seps, n_hint=text.size)
+        with pytest.raises(binding.DebwtError):
+            b.build()
+        with pytest.raises(binding.DebwtError):
+            b.ingest([text[:100]], seps)                    # separators do not match what was streamed

@@ -28,7 +28,10 @@ def dumper(tmp_path_factory):
 
 
 def run_dump(exe, path):
+    """records as read by fastx_read; the streaming reader (fastx_stream, what host/deBWT uses) must agree"""
     out = subprocess.run([exe, path], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    out_s = subprocess.run([exe, "-s", path], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert out == out_s
     recs = [tuple(int(x) for x in l.split()) for l in out[:-1]]
     return recs, out[-1]
 
