@@ -68,6 +68,10 @@ class BwtBuilder:
         except Exception:
             pass
 
+    def set_ambiguity_policy(self, resolve: bool, seed: int = 0):
+        """IUPAC codes: reject (default) or resolve to a seeded pseudo-random compatible base (otherTool/transferN.c)"""
+        check(lib().debwt_set_ambiguity_policy(self._h, int(bool(resolve)), seed))
+
     # -- input -------------------------------------------------------------------------------
     def set_records(self, records: Sequence):
         """Per-record host buffers (what a kseq loop yields)."""

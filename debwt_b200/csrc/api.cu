@@ -218,6 +218,13 @@ int debwt_set_sort_config(debwt_ctx* c, int cfg) {
     return old;
 }
 
+int debwt_set_ambiguity_policy(debwt_ctx* c, int resolve, uint64_t seed) {
+    if (!c) FAIL("null context");
+    c->resolve_ambiguous = resolve != 0;
+    c->ambiguity_seed = seed;
+    return 0;
+}
+
 int debwt_set_records(debwt_ctx* c, const char* const* seqs, const uint64_t* lens, uint64_t n_records) {
     if (!c || !seqs || !lens) FAIL("null argument");
     if (bind_device(c->device)) return -1;
@@ -319,7 +326,9 @@ int debwt_build(debwt_ctx* c, int k) {
     } else {
         if (dalloc(pool, &d_text, text_words(n)) || dalloc(pool, &d_err, 4)) return -1;
         CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
-        if (k_pack(ascii, n, d_text, d_err, st)) return -1;
+        PackPolicy pol;
+        pol.resolve = c->resolve_ambiguous; pol.seed = c->ambiguity_seed;
+        if (k_pack(ascii, n, d_text, d_err, st, pol)) return -1;
         if (c->d_ascii) { pool.adopt(c->d_ascii, n + 64); c->d_ascii = nullptr; }
     }
     mark();                                                                     // ev1
@@ -368,7 +377,8 @@ int debwt_build(debwt_ctx* c, int k) {
     u64 h_tot[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (h_err[0]) FAIL("input contains a symbol other than A, C, G, T (either case)");
+    if (h_err[0]) FAIL(c->resolve_ambiguous ? "input contains a symbol that is neither a base nor an IUPAC ambiguity code"
+                                            : "input contains a symbol other than A, C, G, T (either case)");
     if (h_err[1] != R) FAIL("input contains '#' or '$' inside a record (they are reserved for the record separators)");
     BranchTable bt;
     bt.n_branch = h_tot[0]; bt.n_blue = h_tot[1];
@@ -541,7 +551,9 @@ int ingest_flush(debwt_ctx* c, bool final) {
     }
     const int i = g.cur;
     if (full) CUDA_TRY(cudaMemcpyAsync(g.d_stage[i], g.h_stage[i], full, cudaMemcpyHostToDevice, c->st));
-    if (k_pack_words(g.d_stage[i], full, c->d_packed + g.n / 32, nwords, c->d_packed_err, c->st)) return -1;
+    PackPolicy pol;
+    pol.resolve = c->resolve_ambiguous; pol.seed = c->ambiguity_seed; pol.pos_base = g.n;
+    if (k_pack_words(g.d_stage[i], full, c->d_packed + g.n / 32, nwords, c->d_packed_err, c->st, pol)) return -1;
     CUDA_TRY(cudaEventRecord(g.done[i], c->st));
     g.busy[i] = true;
     g.n += full;

@@ -101,6 +101,8 @@ struct debwt_ctx {
         u64 n = 0;                                 // symbols packed so far (a multiple of 32 until the end)
         u64 cap_words = 0;
     } ing;
+    bool resolve_ambiguous = false;   // debwt_set_ambiguity_policy
+    u64 ambiguity_seed = 0;
     u64* d_packed = nullptr;          // packed text produced by the ingest (skips K1 in the build)
     u32* d_packed_err = nullptr;
     // result

@@ -40,6 +40,6 @@ int k_fill_range(const u16* gmask, u64 n_keys, u64 key_base, u64 n, const u64* s
 int k_emit_blue_base(const u64* blue, BranchTable bt, u64 key_base, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
                      u32* d_sharp_count, u64* dollar_row, cudaStream_t st);
 // K1 on a slice: packs n symbols into nwords words (T padding for [n, n+32), zeros beyond)
-int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cudaStream_t st);
+int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cudaStream_t st, PackPolicy pol = PackPolicy());
 
 }  // namespace debwt

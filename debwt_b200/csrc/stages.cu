@@ -103,20 +103,53 @@ int scan_exclusive_u32(const u32* in, u32* out, u64 m, bool popc, void* workspac
 // =============================================================================================
 namespace {
 
-__device__ __forceinline__ u32 base_code(u32 c, u32& bad, u32& nsep) {
+// IUPAC ambiguity codes -> one of the bases they stand for: the tables of the reference's pre-processing tool
+// (reference otherTool/transferN.c:8-10,17-27: N ACGT, V ACG, D ATG, B TCG, H ATC, W AT, S CG, K TG, M AC, Y CT, R AG), with its
+// rand() replaced by a splitmix64 value of (seed, symbol position): the same input and seed always give the same text.
+__device__ __forceinline__ u32 resolve_ambiguous(u32 u /* upper case */, u64 seed, u64 pos, bool& known) {
+    u32 set;                                          // up to four 2-bit base codes, lowest first; count in bits 8..10
+    switch (u) {
+        case 'N': set = 0xE4u | (4u << 8); break;     // A C G T
+        case 'V': set = 0x24u | (3u << 8); break;     // A C G
+        case 'D': set = 0x2Cu | (3u << 8); break;     // A T G
+        case 'B': set = 0x27u | (3u << 8); break;     // T C G
+        case 'H': set = 0x1Cu | (3u << 8); break;     // A T C
+        case 'W': set = 0x0Cu | (2u << 8); break;     // A T
+        case 'S': set = 0x09u | (2u << 8); break;     // C G
+        case 'K': set = 0x0Bu | (2u << 8); break;     // T G
+        case 'M': set = 0x04u | (2u << 8); break;     // A C
+        case 'Y': set = 0x0Du | (2u << 8); break;     // C T
+        case 'R': set = 0x08u | (2u << 8); break;     // A G
+        default: known = false; return 3u;
+    }
+    known = true;
+    u64 z = seed + (pos + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const u32 pick = (u32)(z % (u64)(set >> 8));
+    return (set >> (2 * pick)) & 3u;
+}
+
+__device__ __forceinline__ u32 base_code(u32 c, u32& bad, u32& nsep, const PackPolicy& pol, u64 pos) {
     // A/a C/c G/g T/t -> 0 1 2 3; '#' '$' (separators) are stored as T like the reference does
     u32 u = c & 0xDFu;
     u32 code = (u >> 1) & 3u;
     code ^= code >> 1;
     bool ok = (u == 0x41u) | (u == 0x43u) | (u == 0x47u) | (u == 0x54u);
     bool sep = (c == 0x23u) | (c == 0x24u);
-    bad |= (u32)(!ok && !sep);
+    if (!ok && !sep) {
+        bool known = false;
+        if (pol.resolve) code = resolve_ambiguous(u, pol.seed, pol.pos_base + pos, known);
+        if (known) return code;
+        bad |= 1u;
+    }
     nsep += (u32)sep;
     return ok ? code : 3u;
 }
 
 __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii, u64 n, u64* __restrict__ words,
-                                                  u64 nwords, u32* __restrict__ err) {
+                                                  u64 nwords, u32* __restrict__ err, PackPolicy pol) {
     const u64 w = (u64)blockIdx.x * TPB + threadIdx.x;
     if (w >= nwords) return;
     const u64 base = w * 32;
@@ -131,14 +164,14 @@ __global__ void __launch_bounds__(TPB) pack_kernel(const u8* __restrict__ ascii,
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 u32 c = (v[q] >> (8 * r)) & 255u;
-                out = (out << 2) | base_code(c, bad, nsep);
+                out = (out << 2) | base_code(c, bad, nsep, pol, base + 4 * q + r);
             }
         }
     } else {
         for (int j = 0; j < 32; ++j) {
             u64 i = base + j;
             u32 code = (i < n + 32) ? 3u : 0u;      // exactly 32 T of padding past the end (src/collect#$.c:87-90)
-            if (i < n) code = base_code(ascii[i], bad, nsep);
+            if (i < n) code = base_code(ascii[i], bad, nsep, pol, i);
             out = (out << 2) | code;
         }
     }
@@ -247,17 +280,17 @@ __global__ void __launch_bounds__(TPB) rle_write_kernel(const u64* __restrict__ 
 
 }  // namespace
 
-int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st) {
+int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st, PackPolicy pol) {
     const u64 nw = text_words(n);
-    pack_kernel<<<grid_for(nw, TPB), TPB, 0, st>>>(ascii, n, words, nw, d_err);
+    pack_kernel<<<grid_for(nw, TPB), TPB, 0, st>>>(ascii, n, words, nw, d_err, pol);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cudaStream_t st) {
+int k_pack_words(const u8* ascii, u64 n, u64* words, u64 nwords, u32* d_err, cudaStream_t st, PackPolicy pol) {
     if (nwords == 0) return 0;
-    pack_kernel<<<grid_for(nwords, TPB), TPB, 0, st>>>(ascii, n, words, nwords, d_err);
+    pack_kernel<<<grid_for(nwords, TPB), TPB, 0, st>>>(ascii, n, words, nwords, d_err, pol);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

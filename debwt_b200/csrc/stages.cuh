@@ -11,7 +11,14 @@ int scan_exclusive_u32(const u32* in, u32* out, u64 m, bool popc, void* workspac
 
 // ---- K1 / K2 ------------------------------------------------------------------------------
 // ascii: n bytes (bases, '#' between records, '$' last).  words: ceil((n+32)/32)+1 u64.
-int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st);
+// what K1 does with a symbol that is not A, C, G or T: reject (default), or resolve IUPAC ambiguity codes to a seeded
+// pseudo-random compatible base (reference otherTool/transferN.c); pos_base = text position of ascii[0]
+struct PackPolicy {
+    bool resolve = false;
+    u64 seed = 0;
+    u64 pos_base = 0;
+};
+int k_pack(const u8* ascii, u64 n, u64* words, u32* d_err, cudaStream_t st, PackPolicy pol = PackPolicy());
 inline u64 text_words(u64 n) { return (n + 32 + 31) / 32 + 1; }
 // all in-record 32-mers; key index of window p in record r is p - 32 r.  keys: n - 32 R entries.
 int k_extract(const u64* words, u64 n, const u64* d_seps, u64 n_rec, u64* keys, cudaStream_t st);

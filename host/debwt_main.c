@@ -10,7 +10,8 @@
  *   <out>.#  rows holding '#', ascending
  *   <out>.$  row holding '$'
  * Differences: -j is accepted and ignored (Jellyfish is replaced by on-GPU count-by-sort), -t is
- * accepted and ignored (the work runs on the GPU), -g picks the CUDA device, no temp files.
+ * accepted and ignored (the work runs on the GPU), -g picks the CUDA device, -n <seed> resolves IUPAC ambiguity codes
+ * reproducibly (the reference needs a separate otherTool/transferN pass, which is time-seeded), no temp files.
  *
  * The reference reads the input twice through kseq (src/collect#$.c:37-48, 66-86) before anything else starts.  Here the
  * file is read ONCE and streamed: the reader writes the bases straight into the library's pinned staging window
@@ -24,6 +25,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "../include/debwt_b200.h"
 #include "fastx.h"
@@ -38,6 +40,7 @@ static void usage(void) {
     fprintf(stderr, "-k (optional): k-mer length (from 12 to 32, default 32)\n");
     fprintf(stderr, "-j (optional): accepted for compatibility, ignored (no Jellyfish needed)\n");
     fprintf(stderr, "-g (optional): CUDA device ordinal (default 0)\n");
+    fprintf(stderr, "-n (optional): seed; IUPAC ambiguity codes are replaced by a pseudo-random compatible base (what otherTool/transferN does, reproducibly)\n");
     fprintf(stderr, "reference: sequence in fasta or fastq format (plain or gzip)\n");
 }
 
@@ -55,12 +58,14 @@ static int write_file(const char* path, const void* data, size_t bytes) {
     return 0;
 }
 
-/* ---- context creation on a second thread (CUDA start-up overlaps the first reads) ---- */
-typedef struct { int gpu; debwt_ctx* ctx; int rc; char err[256]; } create_job;
+/* ---- context creation on a second thread: CUDA start-up (context, kernel images) overlaps reading the file ---- */
+typedef struct { int gpu; debwt_ctx* ctx; int rc; char err[256]; volatile int done; } create_job;
 static void* create_thread(void* p) {
     create_job* j = (create_job*)p;
     j->rc = debwt_create(&j->ctx, j->gpu);
     if (j->rc) { strncpy(j->err, debwt_last_error(), sizeof j->err - 1); j->err[sizeof j->err - 1] = 0; }
+    __sync_synchronize();
+    j->done = 1;
     return NULL;
 }
 
@@ -74,7 +79,27 @@ typedef struct {
     uint64_t nrec, sep_cap;
     int pending_sep;           /* the separator after the last record is written once we know whether it is '#' or '$' */
     int failed;
+    /* until the context exists the symbols are parked in ordinary memory */
+    create_job* job;
+    uint64_t hint;
+    char* park;
+    uint64_t park_n, park_cap;
+    int dry;                   /* no device: only the input checks run */
+    int resolve;               /* -n: IUPAC policy */
+    unsigned long long amb_seed;
 } sink_t;
+
+/* the context has come up: open the streaming input and push what was parked */
+static int sink_attach(sink_t* s) {
+    if (s->job->rc) { s->dry = 1; free(s->park); s->park = NULL; return 0; }
+    s->ctx = s->job->ctx;
+    if (s->resolve && debwt_set_ambiguity_policy(s->ctx, 1, s->amb_seed)) return -1;
+    if (debwt_ingest_begin(s->ctx, s->hint)) return -1;
+    if (s->park_n && debwt_ingest_append(s->ctx, s->park, s->park_n)) return -1;
+    free(s->park);
+    s->park = NULL;
+    return 0;
+}
 
 static int sink_room(sink_t* s) {
     if (s->used && debwt_ingest_commit(s->ctx, s->used)) return -1;
@@ -84,7 +109,23 @@ static int sink_room(sink_t* s) {
 }
 
 static int sink_put(sink_t* s, const unsigned char* p, uint64_t n) {
-    if (!s->ctx) { s->n += n; return 0; }           /* dry run (no device): only the input checks */
+    if (s->dry) { s->n += n; return 0; }
+    if (!s->ctx) {
+        if (s->job->done) {
+            if (sink_attach(s)) { s->failed = 1; return 2; }
+            return sink_put(s, p, n);
+        }
+        if (s->park_n + n > s->park_cap) {
+            uint64_t cap = s->park_cap ? s->park_cap : (64u << 20);
+            while (cap < s->park_n + n) cap += cap >> 1;
+            char* q = (char*)realloc(s->park, cap);
+            if (!q) { fprintf(stderr, "out of host memory\n"); s->failed = 1; return 3; }
+            s->park = q; s->park_cap = cap;
+        }
+        memcpy(s->park + s->park_n, p, n);
+        s->park_n += n; s->n += n;
+        return 0;
+    }
     while (n) {
         if (s->used == s->cap && sink_room(s)) { s->failed = 1; return 2; }
         uint64_t m = s->cap - s->used;
@@ -122,13 +163,15 @@ int main(int argc, char* argv[]) {
     if (argc < 4 || (argc & 1) == 1) { usage(); return 1; }
     const char* source = argv[argc - 1];
     const char* obj = NULL;
-    int k = 32, gpu = 0;
+    int k = 32, gpu = 0, resolve = 0;
+    unsigned long long amb_seed = 0;
     for (int i = 1; i < argc - 1; i += 2) {
         if (strcmp(argv[i], "-o") == 0) obj = argv[i + 1];
         else if (strcmp(argv[i], "-t") == 0) {
             if (atoi(argv[i + 1]) == 0) { fprintf(stderr, "thread number must be a number!\n"); return 1; }
         } else if (strcmp(argv[i], "-j") == 0) { /* ignored */
         } else if (strcmp(argv[i], "-g") == 0) gpu = atoi(argv[i + 1]);
+        else if (strcmp(argv[i], "-n") == 0) { resolve = 1; amb_seed = strtoull(argv[i + 1], NULL, 10); }
         else if (strcmp(argv[i], "-k") == 0) {
             k = atoi(argv[i + 1]);
             if (k < 12 || k > 32) { fprintf(stderr, "-k: k-mer length (from 12 to 32, default 32)\n"); return 1; }
@@ -141,6 +184,7 @@ int main(int argc, char* argv[]) {
     remove(obj);
 
     double t0 = now_s();
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);          /* kernel images load with the context, on the second thread */
     create_job job;
     memset(&job, 0, sizeof job);
     job.gpu = gpu;
@@ -158,30 +202,23 @@ int main(int argc, char* argv[]) {
         if (f) { if (fread(magic, 1, 2, f) != 2) magic[0] = 0; fclose(f); }
         if (stat(source, &sb) == 0 && !(magic[0] == 0x1f && magic[1] == 0x8b)) hint = (uint64_t)sb.st_size + 64;
     }
-    pthread_join(th, NULL);
-    if (job.rc) {
-        /* no usable device: still report what is wrong with the input first, like the reference's first pass does */
-        sink_t dry;
-        memset(&dry, 0, sizeof dry);
-        int drc = fastx_stream(fx, on_bases, on_record, &dry);
-        if (drc < 0) fprintf(stderr, "malformed input file\n");
-        else if (drc == 0 && dry.nrec == 0) fprintf(stderr, "no sequence found in %s\n", source);
-        if (drc == 0 && dry.nrec) fprintf(stderr, "deBWT: %s\n", job.err);
-        return 1;
-    }
-    debwt_ctx* ctx = job.ctx;
-    double t_ctx = now_s();
-    if (debwt_ingest_begin(ctx, hint)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
-
     sink_t s;
     memset(&s, 0, sizeof s);
-    s.ctx = ctx;
+    s.job = &job;
+    s.hint = hint;
+    s.resolve = resolve;
+    s.amb_seed = amb_seed;
     int rc = fastx_stream(fx, on_bases, on_record, &s);
     fastx_close(fx);
-    if (rc == 2 || s.failed) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+    pthread_join(th, NULL);                               /* never leave while CUDA is still starting up */
     if (rc == 3) return 1;
     if (rc < 0) { fprintf(stderr, "malformed input file\n"); return 1; }
-    if (s.nrec == 0) { fprintf(stderr, "no sequence found in %s\n", source); return 1; }
+    if (rc == 0 && s.nrec == 0 && !s.failed) { fprintf(stderr, "no sequence found in %s\n", source); return 1; }
+    if (job.rc) { fprintf(stderr, "deBWT: %s\n", job.err); return 1; }                /* input is fine, but there is no device */
+    if (!s.ctx && !s.failed && sink_attach(&s)) s.failed = 1;                        /* a file shorter than the start-up */
+    if (rc == 2 || s.failed) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
+    debwt_ctx* ctx = s.ctx;
+    double t_ctx = now_s();
     {
         const unsigned char c = '$';                       /* the last separator is '$' (src/collect#$.c:83) */
         if (sink_put(&s, &c, 1)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
@@ -189,8 +226,9 @@ int main(int argc, char* argv[]) {
     if (s.used && debwt_ingest_commit(ctx, s.used)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
     if (debwt_ingest_end(ctx, s.seps, s.nrec)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
     double t1 = now_s();
-    fprintf(stderr, "BWTLEN=%llu (%llu records), context %.3f s, read + parse + upload + pack %.3f s\n", (unsigned long long)s.n,
-            (unsigned long long)s.nrec, t_ctx - t0, t1 - t_ctx);
+    fprintf(stderr, "BWTLEN=%llu (%llu records), read + parse + upload + pack %.3f s (CUDA start-up overlapped; %llu MB parked meanwhile)\n",
+            (unsigned long long)s.n, (unsigned long long)s.nrec, t1 - t0, (unsigned long long)(s.park_n >> 20));
+    (void)t_ctx;
 
     if (debwt_build(ctx, k)) { fprintf(stderr, "deBWT: %s\n", debwt_last_error()); return 1; }
     uint64_t nsym = 0, nwords = 0, nsharp = 0, dollar = 0;
@@ -216,7 +254,8 @@ int main(int argc, char* argv[]) {
     fprintf(stderr, "GPU build + download %.3f s (device %.1f ms: sort %.1f ms, %u launches), write %.3f s; branch k-mers %llu, blue %llu, SP codes %llu\n",
             t2 - t1, st.ms_total, st.ms_sort, st.total_launches, t3 - t2, (unsigned long long)st.n_branch,
             (unsigned long long)st.n_blue, (unsigned long long)st.n_codes);
-    debwt_host_free(bwt);
-    debwt_destroy(ctx);
-    return 0;
+    /* the three files are written and closed: leave without tearing the 56 GB arena and the CUDA context down piece by
+       piece (the reference ends with exit(0) right after its fwrite()s too, src/insertCase3.c:137) */
+    fflush(NULL);
+    _exit(0);
 }

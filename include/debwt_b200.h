@@ -67,6 +67,13 @@ void debwt_destroy(debwt_ctx* ctx);
 /* tuning knob for the sort kernel configuration (0 = default); returns the previous value */
 int debwt_set_sort_config(debwt_ctx* ctx, int cfg);
 
+/* What to do with symbols other than A, C, G, T.  resolve = 0 (default): the build fails, like the reference asks of its
+   input ("make sure your sequence don't contain any uncertain characters like 'N'", src/main.c:178).  resolve = 1: IUPAC
+   ambiguity codes are replaced during K1 by one of the bases they stand for -- the tables of the reference's
+   pre-processing tool (otherTool/transferN.c:8-27), with its time-seeded rand() replaced by splitmix64(seed, position),
+   so that the same input and seed always give the same BWT; anything else still fails.  Set before the input. */
+int debwt_set_ambiguity_policy(debwt_ctx* ctx, int resolve, uint64_t seed);
+
 /* ---- input: replaces collect()'s FASTA pass, src/collect#$.c:27-90 ---------------------------- */
 /* Host records: `seqs[i]` points at `lens[i]` bases (ACGT, either case; no terminator needed).
    Every record must be longer than 32 bp (src/collect#$.c:41-45) and contain only ACGT.

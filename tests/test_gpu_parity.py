@@ -303,3 +303,61 @@ def test_streaming_ingest_large_and_errors():
             b.build()
         with pytest.raises(binding.DebwtError):
             b.ingest([text[:100]], seps)                    # separators do not match what was streamed
+
+
+# ---- f3: seeded IUPAC policy (debwt_set_ambiguity_policy) ---------------------------------------------------------------
+def test_ambiguity_policy_matches_restatement():
+    rng = np.random.default_rng(9)
+    recs = [synth.random_bases(31, 60_000), synth.random_bases(32, 45_001)]
+    text, seps = api.join_records(recs)
+    codes = np.frombuffer(b"NVDBHWSKMYRnvdbhwskmyr", dtype=np.uint8)
+    hits = rng.choice(np.setdiff1d(np.arange(text.size), seps.astype(np.int64)), size=4000, replace=False)
+    amb = text.copy()
+    amb[hits] = codes[rng.integers(0, codes.size, size=hits.size)]
+    with api.BwtBuilder() as b:
+        b.set_text(amb, seps)
+        with pytest.raises(DebwtError):                      # default policy: reject, like the reference asks of its input
+            b.build()
+        for seed in (0, 12345):
+            resolved = st.resolve_ambiguity(amb, seed)
+            assert not (resolved == amb)[hits].any() and (resolved != amb).sum() == hits.size
+            b.set_ambiguity_policy(True, seed)
+            b.set_text(amb, seps)
+            b.build()
+            got = b.result()
+            assert b.verify(resolved)[0] == 0                # the BWT is the BWT of the resolved text ...
+            b.ingest([amb[:33_333], amb[33_333:]], seps)     # ... also when the text is streamed in (positions carry over)
+            b.build()
+            assert all((x == y).all() for x, y in zip(got, b.result()))
+            b.set_ambiguity_policy(False)
+            b.set_text(resolved, seps)
+            b.build()
+            assert all((x == y).all() for x, y in zip(got, b.result()))
+        b.set_ambiguity_policy(True, 1)
+        junk = amb.copy()
+        junk[777] = ord("!")
+        b.set_text(junk, seps)
+        with pytest.raises(DebwtError):
+            b.build()
+
+
+# ---- f4: many short records (the sentinel-window suffixes go through the bitonic network beyond 512 records) ----------
+@pytest.mark.parametrize("n_rec", [600, 3000])
+def test_many_records_gpu_sentinel_sort(n_rec):
+    rng = np.random.default_rng(n_rec)
+    base = synth.random_bases(41, 400)
+    recs = []
+    for i in range(n_rec):
+        r = base[: int(rng.integers(40, 400))].copy() if i % 3 else synth.random_bases(1000 + i, int(rng.integers(33, 200)))
+        if i % 7 == 0 and r.size > 50:
+            r[int(rng.integers(0, r.size))] = ord("A")
+        recs.append(r)
+    text, seps = api.join_records(recs)
+    with api.BwtBuilder() as b:
+        b.set_text(text, seps)
+        b.build()
+        words, sharp, dollar = b.result()
+        assert b.verify(text)[0] == 0
+    sym, _ = st.text_from_records([bytes(r) for r in recs])
+    ow, os_, od = coracle.bwt(sym)
+    assert (words == ow).all() and (sharp == os_).all() and (dollar == od).all()
