@@ -246,3 +246,26 @@ def verify_bwt_device(bwt_ptr: int, n_symbols: int, sharp_rows: np.ndarray, doll
     check(lib().debwt_verify_bwt_device(device, c_p(bwt_ptr), n_symbols, _ptr(sharp), sharp.size, int(dollar_row), c_p(text_ptr),
                                         ctypes.byref(bad), ctypes.byref(ms)))
     return int(bad.value), float(ms.value)
+
+
+def k_codes(text: np.ndarray, seps: np.ndarray, device: int = 0):
+    """K9: (codes u8[S], blue entries as (group head key index u64[M], spIndex u64[M], prev u8[M]))"""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    seps = np.ascontiguousarray(seps, dtype=np.uint64)
+    cap = text.size + 64
+    codes = np.empty(cap, dtype=np.uint8)
+    head, spi, prev = np.empty(cap, dtype=np.uint64), np.empty(cap, dtype=np.uint64), np.empty(cap, dtype=np.uint8)
+    nc, nb = c_u64(), c_u64()
+    check(lib().debwt_k_codes(device, _ptr(text), text.size, _ptr(seps), seps.size, _ptr(codes), cap, ctypes.byref(nc), _ptr(head),
+                              _ptr(spi), _ptr(prev), cap, ctypes.byref(nb)))
+    return codes[:nc.value].copy(), head[:nb.value].copy(), spi[:nb.value].copy(), prev[:nb.value].copy()
+
+
+def k_sort_blue(codes: np.ndarray, seg_offsets: np.ndarray, spindex: np.ndarray, prev: np.ndarray, device: int = 0):
+    """K10 alone: returns (spindex, prev) with every segment ordered by its code strings"""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    offs = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
+    spi = np.ascontiguousarray(spindex, dtype=np.uint64).copy()
+    prv = np.ascontiguousarray(prev, dtype=np.uint8).copy()
+    check(lib().debwt_k_sort_blue(device, _ptr(codes), codes.size, _ptr(offs), offs.size - 1, _ptr(spi), _ptr(prv)))
+    return spi, prv

@@ -459,6 +459,22 @@ int debwt_build(debwt_ctx* c, int k) {
     CUDA_TRY(cudaStreamSynchronize(st));
     mark();                                                                     // ev6
 
+    if (c->cap.on) {                     // debwt_k_codes: hand the K9 products to the test before K10 reorders the entries
+        auto& q = c->cap;
+        q.codes.resize(ncw); q.sep.resize(ncw + 1); q.blue.resize(bt.n_blue); q.seg_off.resize(bt.n_branch + 1);
+        q.seg_head.resize(bt.n_branch); q.seg_kmer.resize(bt.n_branch);
+        q.dollar_index = dollar_index; q.n_codes = n_codes;
+        CUDA_TRY(cudaMemcpyAsync(q.codes.data(), d_codes, ncw * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(q.sep.data(), d_sep, (ncw + 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (bt.n_blue) CUDA_TRY(cudaMemcpyAsync(q.blue.data(), d_blue, bt.n_blue * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(q.seg_off.data(), bt.blue, (bt.n_branch + 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (bt.n_branch) {
+            CUDA_TRY(cudaMemcpyAsync(q.seg_head.data(), bt.head, bt.n_branch * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(q.seg_kmer.data(), bt.kmer, bt.n_branch * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+
     // ---- K10 segmented sort ----
     u32* d_work = nullptr;
     if (dalloc(pool, &d_work, 4 * bt.n_branch + 16)) return -1;
@@ -796,6 +812,82 @@ int debwt_k_group_masks(int device, const char* text, uint64_t n, const uint64_t
         return -1;
     CUDA_TRY(cudaMemcpyAsync(masks_out, d_g, nk * 2, cudaMemcpyDeviceToHost, s.st));
     CUDA_TRY(cudaStreamSynchronize(s.st));
+    return 0;
+}
+
+
+// K9 through the production build: SP codes (0..3, 4 = '#', 5 = '$') and the blue entries before K10
+int debwt_k_codes(int device, const char* text, uint64_t n, const uint64_t* seps, uint64_t R, uint8_t* codes_out, uint64_t codes_cap,
+                  uint64_t* n_codes_out, uint64_t* blue_head_out, uint64_t* blue_spindex_out, uint8_t* blue_prev_out, uint64_t blue_cap,
+                  uint64_t* n_blue_out) {
+    debwt_ctx* c = nullptr;
+    if (debwt_create(&c, device)) return -1;
+    c->cap.on = true;
+    int rc = debwt_set_text(c, text, n, seps, R);
+    if (!rc) rc = debwt_build(c, 32);
+    if (!rc) {
+        const auto& q = c->cap;
+        if (n_codes_out) *n_codes_out = q.n_codes;
+        if (n_blue_out) *n_blue_out = q.blue.size();
+        if (q.n_codes > codes_cap || q.blue.size() > blue_cap) { set_error("debwt_k_codes: output buffers too small"); rc = -1; }
+    }
+    if (!rc) {
+        const auto& q = c->cap;
+        for (u64 i = 0; i < q.n_codes; ++i) {
+            u8 code = (u8)((q.codes[i >> 5] >> (2 * (31 - (i & 31)))) & 3ull);
+            if ((q.sep[i >> 5] >> (i & 31)) & 1u) code = i == q.dollar_index ? 5 : 4;
+            codes_out[i] = code;
+        }
+        for (u64 b = 0; b < q.seg_kmer.size(); ++b)
+            for (u32 e = q.seg_off[b]; e < q.seg_off[b + 1]; ++e) {
+                blue_head_out[e] = q.seg_head[b];
+                blue_spindex_out[e] = q.blue[e] >> 4;
+                blue_prev_out[e] = (u8)(q.blue[e] & 15ull);
+            }
+    }
+    debwt_destroy(c);
+    return rc;
+}
+
+// K10 alone: codes (one byte per code, 0..3, 4 = '#', 5 = '$' which must be the last code and unique), segments of
+// (spIndex, prev) entries; sorts every segment by the code string starting at spIndex (cmpSP, src/sortBlue.c:109-173)
+int debwt_k_sort_blue(int device, const uint8_t* codes, uint64_t n_codes, const uint64_t* seg_offsets, uint64_t n_segments,
+                      uint64_t* spindex_inout, uint8_t* prev_inout) {
+    Scratch s;
+    if (open_scratch(s, device)) return -1;
+    const u64 M = seg_offsets[n_segments];
+    if (M >= 0xFFFFFFFFull) FAIL("too many entries");
+    const u64 ncw = n_codes / 32 + 3;
+    std::vector<u64> h_codes(ncw, 0);
+    std::vector<u32> h_sep(ncw + 1, 0);
+    u64 dollar = 0;
+    for (u64 i = 0; i < n_codes; ++i) {
+        const u8 cd = codes[i];
+        if (cd > 5) FAIL("code out of range");
+        h_codes[i >> 5] |= (u64)(cd > 3 ? 3 : cd) << (2 * (31 - (i & 31)));      // separators are stored as T (src/generateSP.c:630-642)
+        if (cd > 3) { h_sep[i >> 5] |= 1u << (i & 31); if (cd == 5) dollar = i; }
+    }
+    std::vector<u64> h_blue(M + 1), h_kmer(n_segments + 1);
+    std::vector<u32> h_off(n_segments + 2);
+    for (u64 e = 0; e < M; ++e) h_blue[e] = (spindex_inout[e] << 4) | prev_inout[e];
+    for (u64 b = 0; b < n_segments; ++b) { h_kmer[b] = (b << 2) | 2ull; h_off[b] = (u32)seg_offsets[b]; }
+    h_off[n_segments] = (u32)M;
+    u64 *d_codes, *d_blue, *d_kmer; u32 *d_sep, *d_off, *d_work;
+    if (s.get(&d_codes, ncw) || s.get(&d_sep, ncw + 1) || s.get(&d_blue, M + 1) || s.get(&d_kmer, n_segments + 1) ||
+        s.get(&d_off, n_segments + 2) || s.get(&d_work, 4 * n_segments + 16))
+        return -1;
+    CUDA_TRY(cudaMemcpyAsync(d_codes, h_codes.data(), ncw * 8, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(d_sep, h_sep.data(), (ncw + 1) * 4, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(d_blue, h_blue.data(), (M + 1) * 8, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(d_kmer, h_kmer.data(), (n_segments + 1) * 8, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, h_off.data(), (n_segments + 2) * 4, cudaMemcpyHostToDevice, s.st));
+    BranchTable bt;
+    bt.n_branch = n_segments; bt.n_blue = M; bt.kmer = d_kmer; bt.blue = d_off;
+    SpView spv{d_codes, d_sep, dollar, n_codes};
+    if (k_sort_blue(d_blue, bt, spv, d_work, s.st)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(h_blue.data(), d_blue, M * 8, cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaStreamSynchronize(s.st));
+    for (u64 e = 0; e < M; ++e) { spindex_inout[e] = h_blue[e] >> 4; prev_inout[e] = (u8)(h_blue[e] & 15ull); }
     return 0;
 }
 

@@ -101,6 +101,17 @@ struct debwt_ctx {
         u64 n = 0;                                 // symbols packed so far (a multiple of 32 until the end)
         u64 cap_words = 0;
     } ing;
+    // debwt_k_codes: the build copies the K9 products to the host right before K10 (test entry point only)
+    struct Capture {
+        bool on = false;
+        std::vector<u64> codes;        // packed 2-bit SP codes
+        std::vector<u32> sep;          // 1 bit per code: '#' / '$'
+        u64 dollar_index = 0, n_codes = 0;
+        std::vector<u64> blue;         // (spIndex << 4) | prev, grouped by segment, unsorted inside
+        std::vector<u32> seg_off;      // n_branch + 1 offsets into blue
+        std::vector<u32> seg_head;     // sorted-key index of each branch k-mer's group
+        std::vector<u64> seg_kmer;     // (k-mer << 2) | multi_in << 1 | multi_out
+    } cap;
     bool resolve_ambiguous = false;   // debwt_set_ambiguity_policy
     u64 ambiguity_seed = 0;
     u64* d_packed = nullptr;          // packed text produced by the ingest (skips K1 in the build)

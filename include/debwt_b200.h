@@ -167,6 +167,18 @@ int debwt_k_rle(int device, const uint64_t* sorted, uint64_t n, uint64_t* kmers_
 int debwt_k_group_masks(int device, const char* text, uint64_t n_symbols, const uint64_t* seps, uint64_t n_records,
                         uint16_t* masks_out /* n - 32 R */);
 
+/* K9 through the production build (src/generateSP.c:534-683): the branch ("SP") codes, one byte each -- 0..3 the next
+   base, 4 = '#', 5 = '$' -- and the blue entries as K10 receives them: for entry e the sorted-key index of its k-mer's
+   group, its spIndex and its previous symbol (0..3, 4 = '#', 5 = '$'), grouped by k-mer, any order inside a group. */
+int debwt_k_codes(int device, const char* text, uint64_t n_symbols, const uint64_t* seps, uint64_t n_records, uint8_t* codes_out,
+                  uint64_t codes_cap, uint64_t* n_codes_out, uint64_t* blue_head_out, uint64_t* blue_spindex_out,
+                  uint8_t* blue_prev_out, uint64_t blue_cap, uint64_t* n_blue_out);
+/* K10 alone (src/sortBlue.c:76-280): codes as above ('$' exactly once, as the last code); segment i = entries
+   seg_offsets[i] .. seg_offsets[i+1]); every segment is ordered by the code string starting at its entries' spIndex,
+   in place.  Runs whose previous symbols are all equal may keep any order (src/sortBlue.c:192-219). */
+int debwt_k_sort_blue(int device, const uint8_t* codes, uint64_t n_codes, const uint64_t* seg_offsets, uint64_t n_segments,
+                      uint64_t* spindex_inout, uint8_t* prev_inout);
+
 /* Device-resident sort benchmark helper: sorts `n` pseudo-random keys `iters` times on the device
    (keys regenerated on device before each run) and returns the mean device ms per sort. */
 int debwt_bench_sort(int device, uint64_t n, int cfg, int iters, float* ms_out);
