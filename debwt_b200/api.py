@@ -14,7 +14,7 @@ from typing import Sequence
 import numpy as np
 
 from . import binding
-from .binding import DebwtError, Stats, c_p, c_u64, check, lib
+from .binding import DebwtError, ShardStats, Stats, c_p, c_u64, check, lib
 
 
 def _ptr(a: np.ndarray):
@@ -269,3 +269,95 @@ def k_sort_blue(codes: np.ndarray, seg_offsets: np.ndarray, spindex: np.ndarray,
     prv = np.ascontiguousarray(prev, dtype=np.uint8).copy()
     check(lib().debwt_k_sort_blue(device, _ptr(codes), codes.size, _ptr(offs), offs.size - 1, _ptr(spi), _ptr(prv)))
     return spi, prv
+
+
+def verify_walk_device(bwt_ptr: int, n_symbols: int, sharp_rows: np.ndarray, dollar_row: int, tail_ptr: int, steps: int, device: int = 0):
+    """sequential LF walk of `steps` rows from the '$' row against the last `steps` symbols of T (device pointers);
+    returns (mismatches, C-array).  For texts beyond the list-ranking verifier's 2^32 symbols."""
+    sharp = np.ascontiguousarray(sharp_rows, dtype=np.uint64)
+    bad = c_u64()
+    carr = np.zeros(6, dtype=np.uint64)
+    check(lib().debwt_verify_walk_device(device, c_p(bwt_ptr), n_symbols, _ptr(sharp), sharp.size, int(dollar_row), c_p(tail_ptr), steps,
+                                         ctypes.byref(bad), _ptr(carr)))
+    return int(bad.value), carr
+
+
+# ---- multi-GPU: the sharded build behind the C ABI (csrc/shard.cu) ---------------------------------------------------
+class Shard:
+    """One rank of the sharded build (one per GPU; a process under torchrun, or a thread)."""
+
+    def __init__(self, device: int, rank: int, world: int, group_tag: str, same_process: bool = False, sort_config: int = 0):
+        self._h = c_p()
+        self.rank, self.world, self.device = rank, world, device
+        check(lib().debwt_shard_create(ctypes.byref(self._h), device, rank, world, group_tag.encode(), int(same_process)))
+        if sort_config:
+            lib().debwt_shard_set_sort_config(self._h, sort_config)
+
+    def close(self):
+        if self._h:
+            lib().debwt_shard_destroy(self._h)
+            self._h = c_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def slice(self, n_symbols: int):
+        lo, hi = c_u64(), c_u64()
+        check(lib().debwt_shard_slice(self.rank, self.world, n_symbols, ctypes.byref(lo), ctypes.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def build(self, slice_ptr: int, on_device: bool, n_symbols: int, seps: np.ndarray):
+        seps = np.ascontiguousarray(seps, dtype=np.uint64)
+        check(lib().debwt_shard_build(self._h, c_p(slice_ptr), int(on_device), n_symbols, _ptr(seps), seps.size))
+        self._n, self._r = n_symbols, int(seps.size)
+
+    def build_host(self, text: np.ndarray, seps: np.ndarray):
+        """every rank passes the whole T; only its slice is read"""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        lo, hi = self.slice(text.size)
+        sl = np.ascontiguousarray(text[lo:hi]) if hi > lo else np.zeros(1, np.uint8)
+        self.build(sl.ctypes.data, False, text.size, seps)
+
+    def result(self):
+        """(words, sharp, dollar) on rank 0, None elsewhere"""
+        if self.rank != 0:
+            check(lib().debwt_shard_result_copy(self._h, c_p(0), c_p(0), c_p(0)))
+            return None
+        words = np.empty((self._n + 31) // 32, dtype=np.uint64)
+        sharp = np.empty(max(self._r - 1, 0), dtype=np.uint64)
+        dollar = np.empty(1, dtype=np.uint64)
+        check(lib().debwt_shard_result_copy(self._h, _ptr(words), _ptr(sharp), _ptr(dollar)))
+        return words, sharp, dollar
+
+    def result_device_ptr(self) -> int:
+        p, nw = c_p(), c_u64()
+        check(lib().debwt_shard_result_device(self._h, ctypes.byref(p), ctypes.byref(nw)))
+        return p.value or 0
+
+    def result_into(self, host_ptr: int):
+        sharp = np.empty(max(self._r - 1, 0), dtype=np.uint64)
+        dollar = np.empty(1, dtype=np.uint64)
+        check(lib().debwt_shard_result_copy(self._h, c_p(host_ptr), _ptr(sharp), _ptr(dollar)))
+        return sharp, dollar
+
+    def stats(self) -> dict:
+        s = ShardStats()
+        check(lib().debwt_shard_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+
+def build_multi(text: np.ndarray, seps: np.ndarray, devices: Sequence[int]):
+    """one process, one thread per GPU (debwt_build_multi): (words, sharp, dollar, stats of rank 0)"""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    seps = np.ascontiguousarray(seps, dtype=np.uint64)
+    devs = (ctypes.c_int * len(devices))(*devices)
+    words = np.empty((text.size + 31) // 32, dtype=np.uint64)
+    sharp = np.empty(seps.size - 1, dtype=np.uint64)
+    dollar = np.empty(1, dtype=np.uint64)
+    st = ShardStats()
+    check(lib().debwt_build_multi(devs, len(devices), _ptr(text), text.size, _ptr(seps), seps.size, _ptr(words), _ptr(sharp), _ptr(dollar),
+                                  ctypes.byref(st)))
+    return words, sharp, dollar, st.as_dict()

@@ -22,6 +22,14 @@ class DebwtError(RuntimeError):
     pass
 
 
+class ShardStats(ctypes.Structure):
+    _fields_ = [(n, c_u64) for n in ("n_symbols", "n_records", "n_keys", "n_keys_local", "n_branch", "n_blue", "n_codes", "arena_bytes")] + \
+               [(n, ctypes.c_float) for n in ("ms_total", "ms_sort", "ms_sort_sweeps")] + [("sort_sweeps", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class Stats(ctypes.Structure):
     _fields_ = [(n, c_u64) for n in ("n_symbols", "n_records", "n_keys", "n_branch", "n_blue", "n_codes", "n_special")] + \
                [(n, ctypes.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_sort_sweeps", "ms_classify", "ms_special",
@@ -55,6 +63,15 @@ _SIGS = {
     "debwt_result_sizes": (ctypes.c_int, [c_p, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
     "debwt_result_copy": (ctypes.c_int, [c_p, c_p, c_p, c_p]),
     "debwt_get_stats": (ctypes.c_int, [c_p, ctypes.POINTER(Stats)]),
+    "debwt_shard_create": (ctypes.c_int, [ctypes.POINTER(c_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
+    "debwt_shard_destroy": (None, [c_p]),
+    "debwt_shard_set_sort_config": (ctypes.c_int, [c_p, ctypes.c_int]),
+    "debwt_shard_slice": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u64, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]),
+    "debwt_shard_build": (ctypes.c_int, [c_p, c_p, ctypes.c_int, c_u64, c_p, c_u64]),
+    "debwt_shard_result_device": (ctypes.c_int, [c_p, ctypes.POINTER(c_p), ctypes.POINTER(c_u64)]),
+    "debwt_shard_result_copy": (ctypes.c_int, [c_p, c_p, c_p, c_p]),
+    "debwt_shard_get_stats": (ctypes.c_int, [c_p, ctypes.POINTER(ShardStats)]),
+    "debwt_build_multi": (ctypes.c_int, [c_p, ctypes.c_int, c_p, c_u64, c_p, c_u64, c_p, c_p, c_p, ctypes.POINTER(ShardStats)]),
     "debwt_index_build": (ctypes.c_int, [c_p]),
     "debwt_index_sizes": (ctypes.c_int, [c_p, ctypes.POINTER(c_u64)]),
     "debwt_index_copy": (ctypes.c_int, [c_p, c_p, c_p]),
@@ -63,6 +80,7 @@ _SIGS = {
     "debwt_verify_text_device": (ctypes.c_int, [c_p, c_p, c_u64, ctypes.POINTER(c_u64), ctypes.POINTER(ctypes.c_float)]),
     "debwt_verify_bwt_device": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_p, c_u64, c_u64, c_p, ctypes.POINTER(c_u64),
                                                 ctypes.POINTER(ctypes.c_float)]),
+    "debwt_verify_walk_device": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_p, c_u64, c_u64, c_p, c_u64, ctypes.POINTER(c_u64), c_p]),
     "debwt_synth_random_bases": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_u64]),
     "debwt_synth_insert_family": (ctypes.c_int, [ctypes.c_int, c_p, c_u64, c_u64, c_u64, c_u64, c_u64, c_p]),
     "debwt_synth_mutate": (ctypes.c_int, [ctypes.c_int, c_p, c_p, c_u64, c_u64, c_u64]),

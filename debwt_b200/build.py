@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdebwt_b200.so")
-SOURCES = ["radix_sort.cu", "radix_sort_tma.cu", "stages.cu", "bluesort.cu", "dist_kernels.cu", "dev_api.cu", "api.cu", "index.cu", "synth.cu"]
-HEADERS = ["common.cuh", "radix_sort.cuh", "radix_common.cuh", "ctx.cuh", "stages.cuh", "stages_dev.cuh", "special.cuh", "dist_kernels.cuh",
+SOURCES = ["radix_sort.cu", "radix_sort_tma.cu", "stages.cu", "bluesort.cu", "dist_kernels.cu", "dev_api.cu", "api.cu", "index.cu", "synth.cu", "shard.cu"]
+HEADERS = ["common.cuh", "radix_sort.cuh", "radix_common.cuh", "ctx.cuh", "shmcomm.h", "stages.cuh", "stages_dev.cuh", "special.cuh", "dist_kernels.cuh",
            os.path.join("..", "..", "include", "debwt_b200.h"), os.path.join("..", "..", "include", "debwt_b200_dev.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     raise RuntimeError("nvcc failed: " + " ".join(cmd))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lrt", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             print(res.stdout + res.stderr)

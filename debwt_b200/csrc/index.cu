@@ -11,6 +11,7 @@
 //     its distance to the end of the walk, i.e. its text position.  The BWT is the BWT of T iff the permutation is ONE
 //     cycle and the symbol of row r equals T[position(r) - 1] for every r -- checked against the caller's ASCII text.
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "ctx.cuh"
@@ -191,6 +192,19 @@ __global__ void __launch_bounds__(TPB) lf_check_kernel(FmView f, const u64* __re
     bool ok = (u32)(a >> 32) == NIL;                                              // reached the end: r is on the one cycle
     if (ok) ok = row_symbol(f, r) == ascii_symbol(text[(u32)a]);
     if (!ok) atomicAdd(bad, 1ull);
+}
+
+// sequential LF walk from the row of suffix 0 (it holds '$'): step i must show T[N-1-i]; one thread, `steps` dependent
+// steps -- the reference's own developer check (src/LFsearch.c:49-166), for texts beyond the list-ranking verifier's 2^32
+__global__ void lf_walk_kernel(FmView f, const u8* __restrict__ tail, u64 steps, unsigned long long* __restrict__ bad) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    u64 r = f.dollar_row;
+    unsigned long long nb = 0;
+    for (u64 i = 0; i < steps; ++i) {
+        if (row_symbol(f, r) != ascii_symbol(tail[steps - 1 - i])) ++nb;
+        r = lf_of(f, r);
+    }
+    *bad = nb;
 }
 
 // backward search of one pattern per thread (count only)
@@ -405,6 +419,41 @@ int debwt_verify_bwt_device(int device, const uint64_t* d_bwt_words, uint64_t n_
     CUDA_TRY(cudaDeviceSynchronize());                    // the caller's buffers may have been produced on another stream
     int rc = index_build_with(&tmp, std::move(sharp), dollar_row);
     if (!rc) rc = verify_indexed(&tmp, d_text, n_bad_out, ms_out);
+    drop_index(&tmp);
+    cudaStreamDestroy(tmp.st);
+    return rc;
+}
+
+int debwt_verify_walk_device(int device, const uint64_t* d_bwt_words, uint64_t n_symbols, const uint64_t* sharp_rows, uint64_t n_sharp,
+                             uint64_t dollar_row, const void* d_text_tail, uint64_t steps, uint64_t* n_bad_out, uint64_t* c_array_out) {
+    if (!d_bwt_words || !d_text_tail || (n_sharp && !sharp_rows)) FAIL("null argument");
+    if (steps > n_symbols) FAIL("verify: more steps than symbols");
+    if (debwt_device_count() <= device || device < 0) FAIL("no such CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    debwt_ctx tmp;
+    tmp.device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&tmp.st, cudaStreamNonBlocking));
+    tmp.n = n_symbols; tmp.n_rec = n_sharp + 1; tmp.n_words = (n_symbols + 31) / 32;
+    tmp.d_bwt = reinterpret_cast<u64*>(const_cast<uint64_t*>(d_bwt_words));
+    tmp.built = true;
+    std::vector<u64> sharp(sharp_rows, sharp_rows + n_sharp);
+    std::sort(sharp.begin(), sharp.end());
+    CUDA_TRY(cudaDeviceSynchronize());
+    int rc = index_build_with(&tmp, std::move(sharp), dollar_row);           // also checks that the base counts add up to N
+    unsigned long long* d_bad = nullptr;
+    if (!rc && cudaMalloc(reinterpret_cast<void**>(&d_bad), 8) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory"); rc = -1; }
+    if (!rc) {
+        lf_walk_kernel<<<1, 32, 0, tmp.st>>>(view_of(&tmp), static_cast<const u8*>(d_text_tail), steps, d_bad);
+        DEBWT_COUNT(1);
+        unsigned long long bad = 0;
+        if (cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, tmp.st) != cudaSuccess || cudaStreamSynchronize(tmp.st) != cudaSuccess) {
+            set_error(std::string("verify walk: ") + cudaGetErrorString(cudaGetLastError()));
+            rc = -1;
+        }
+        if (n_bad_out) *n_bad_out = bad;
+        if (c_array_out) for (int i = 0; i < 6; ++i) c_array_out[i] = tmp.c_array[i];
+    }
+    if (d_bad) cudaFree(d_bad);
     drop_index(&tmp);
     cudaStreamDestroy(tmp.st);
     return rc;

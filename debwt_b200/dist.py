@@ -375,6 +375,13 @@ class CudaOps:
                                                _p(bt["blue"]), _p(cursor), _u64(bt["B"]), _p(blue), self._st()))
         return blue
 
+    def release_cached(self, m):
+        """K10 takes its work lists from the driver's stream-ordered pool, not from torch: for large builds hand torch's
+        cached (free) blocks back first"""
+        if m > (64 << 20):
+            torch.cuda.synchronize(self.device)
+            torch.cuda.empty_cache()
+
     def sort_blue(self, blue, bt, codes, sep, dollar_index, n_codes):
         if bt["M"] == 0:
             return
@@ -410,6 +417,9 @@ class CudaOps:
 
     def sync(self):
         torch.cuda.synchronize(self.device)
+
+    def free_gib(self):
+        return torch.cuda.mem_get_info(self.device)[0] / 2**30
 
 
 def special_tables_host(info_np, ins_by_t, seps_np, n_rec):
@@ -575,6 +585,8 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     def tick(name):
         if stats is not None and stats.get("profile"):
             ops.sync()
+            if hasattr(ops, "free_gib"):
+                phases["min_free_gib"] = min(phases.get("min_free_gib", 1e9), ops.free_gib())
             now = _time.perf_counter()
             phases[name] = phases.get(name, 0.0) + (now - _t[0]) * 1e3
             _t[0] = now
@@ -703,11 +715,16 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     d_bbase = ops.from_numpy(b_base)
     db = ops.owner_of_index(rec_index, d_bbase, G) if rec_index.numel() else ops.empty(0, torch.uint8)
     e_part, i_part, rcounts = ops.partition(rec_entry, rec_index, db, G)
+    del rec_entry, rec_index, db, mo, wpfx          # at 30 Gbp every one of these is gigabytes per rank
     e_recv, _ = comm.all_to_all_v(e_part, rcounts)
+    del e_part
     i_recv, _ = comm.all_to_all_v(i_part, rcounts)
+    del i_part
     if int(e_recv.numel()) != bt["M"]:
         raise binding.DebwtError("internal: blue entry exchange mismatch")
     blue = ops.scatter_blue(e_recv, i_recv, bt)
+    del e_recv, i_recv
+    ops.release_cached(bt["M"])
     ops.sort_blue(blue, bt, codes, sep, dollar_index, s_tot)
 
     tick('blue')

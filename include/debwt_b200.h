@@ -116,6 +116,39 @@ int debwt_result_sizes(const debwt_ctx* ctx, uint64_t* n_symbols, uint64_t* n_wo
 int debwt_result_copy(debwt_ctx* ctx, uint64_t* bwt_words, uint64_t* sharp_rows, uint64_t* dollar_row);
 int debwt_get_stats(const debwt_ctx* ctx, debwt_stats* out);
 
+/* ---- multi-GPU: the sharded build, one rank per GPU (the reference has no distributed code) ----------
+   SPMD: every rank -- a process started by torchrun / mpirun, or a thread -- creates its shard with the same group tag,
+   passes ITS position slice of T (debwt_shard_slice) and the same separators to debwt_shard_build, and rank 0 ends up with
+   the whole result.  Keys are range-partitioned by sampled splitters and stored straight into their owner's memory over
+   NVLink; each rank sorts / classifies its key range and emits its own contiguous BWT segment.  same_process = 1 when the
+   ranks are threads of one process (peer access instead of CUDA IPC). */
+typedef struct debwt_shard debwt_shard;
+typedef struct debwt_shard_stats {
+    uint64_t n_symbols, n_records, n_keys;
+    uint64_t n_keys_local;   /* keys this rank owns after the exchange */
+    uint64_t n_branch, n_blue, n_codes;
+    uint64_t arena_bytes;    /* HBM held by this rank's arena (shared exchange buffers not included) */
+    float ms_total;          /* CUDA events on this rank's stream around the whole build */
+    float ms_sort, ms_sort_sweeps;
+    uint32_t sort_sweeps;
+} debwt_shard_stats;
+int debwt_shard_create(debwt_shard** out, int device, int rank, int world, const char* group_tag, int same_process);
+void debwt_shard_destroy(debwt_shard* shard);
+int debwt_shard_set_sort_config(debwt_shard* shard, int cfg);
+/* [lo, hi) of T that rank `rank` of `world` uploads and works on */
+int debwt_shard_slice(int rank, int world, uint64_t n_symbols, uint64_t* lo, uint64_t* hi);
+/* collective; slice = T[lo .. hi) as ASCII, host or device memory */
+int debwt_shard_build(debwt_shard* shard, const void* slice, int slice_on_device, uint64_t n_symbols, const uint64_t* seps,
+                      uint64_t n_records);
+/* rank 0 holds the result (other ranks: no-ops / NULL) */
+int debwt_shard_result_device(const debwt_shard* shard, const uint64_t** d_bwt_words, uint64_t* n_words);
+int debwt_shard_result_copy(debwt_shard* shard, uint64_t* bwt_words, uint64_t* sharp_rows, uint64_t* dollar_row);
+int debwt_shard_get_stats(const debwt_shard* shard, debwt_shard_stats* out);
+/* One call, one process, one thread per GPU: T in host memory in, the reference's three outputs out
+   (what `deBWT -g 0,1,2,...` runs).  Replaces mySort .. insertCase3 (src/main.c:83-149) on several GPUs. */
+int debwt_build_multi(const int* devices, int n_devices, const char* text, uint64_t n_symbols, const uint64_t* seps,
+                      uint64_t n_records, uint64_t* bwt_words, uint64_t* sharp_rows, uint64_t* dollar_row, debwt_shard_stats* stats_out);
+
 /* ---- FM-index tables over the result: the reference's "developer mode", src/insertCase3.c:139-208 ---------- */
 /* occ checkpoints every 32 rows in the reference's layout -- occ[(N >> 5) + 1][4] u64, occ[w][c] = rows < 32 w holding
    base c, rows holding '#'/'$' (stored as T) not counted -- and the C-array (src/collect#$.c:92-100).  Built on the
@@ -138,6 +171,12 @@ int debwt_verify_text_device(debwt_ctx* ctx, const void* d_text, uint64_t n_symb
    reference's .# / .$ files. */
 int debwt_verify_bwt_device(int device, const uint64_t* d_bwt_words, uint64_t n_symbols, const uint64_t* sharp_rows, uint64_t n_sharp,
                             uint64_t dollar_row, const void* d_text, uint64_t* n_bad_out, float* ms_out);
+
+/* For texts beyond 2^32 symbols (C5): the occ / C tables of the packed BWT (their totals must add up to N) and a sequential
+   LF walk of `steps` rows from the row holding '$' -- the reference's developer check, src/LFsearch.c:49-166 --, which must
+   spell the last `steps` symbols of T backwards (d_text_tail: those symbols, ASCII, on the device).  c_array_out: 6 u64. */
+int debwt_verify_walk_device(int device, const uint64_t* d_bwt_words, uint64_t n_symbols, const uint64_t* sharp_rows, uint64_t n_sharp,
+                             uint64_t dollar_row, const void* d_text_tail, uint64_t steps, uint64_t* n_bad_out, uint64_t* c_array_out);
 
 /* ---- synthetic workloads on the device (bench / test plumbing; bit-identical to debwt_b200/synth.py) ------ */
 /* n iid-uniform bases (ASCII) of the splitmix64 stream `seed` into device memory */

@@ -339,6 +339,9 @@ class NumpyOps:
                 seg = sorted(bl[lo:hi].tolist(), key=lambda e: sb[(e >> 4):])
                 bl[lo:hi] = seg
 
+    def release_cached(self, m):
+        pass
+
     def bwt_segment(self, word_lo, word_hi):
         """numpy restatement: the segment is a view into a full-size array, which is also the handle"""
         full = torch.zeros(word_hi + 2, dtype=torch.int64)
