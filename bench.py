@@ -435,8 +435,8 @@ def ours(args, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------------
 # our arm, N GPUs
 # ------------------------------------------------------------------------------------------------
-def ours_sharded(args, rank, world, local_rank):
-    """N GPUs, one process per GPU: the text is split by position, keys are range-partitioned by sampled splitters and
+def ours_sharded_python(args, rank, world, local_rank):
+    """(--orchestrator python: debwt_b200/dist.py, the CPU-testable harness)  N GPUs, one process per GPU: the text is split by position, keys are range-partitioned by sampled splitters and
     exchanged over NVLink (debwt_b200/dist.py).  Strong scaling: the same genome on N GPUs."""
     import numpy as np
     import torch
@@ -565,6 +565,130 @@ def ours_sharded(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def ours_shard(args, rank, world, local_rank):
+    """N GPUs, one process per GPU, the sharded build behind the C ABI (csrc/shard.cu: debwt_shard_*): the text is split by
+    position, keys are range-partitioned by sampled splitters and stored into their owner's memory over NVLink, every rank
+    emits its own BWT segment.  Strong scaling: the same genome on N GPUs.  torch.distributed (NCCL) is only the bench's own
+    barrier / max-over-ranks plumbing."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from debwt_b200 import api, binding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tag = [f"b{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}_{time.time_ns() & 0xffffff}"]
+    if world > 1:
+        dist.broadcast_object_list(tag, src=0)
+    sh = api.Shard(local_rank, rank, world, tag[0], sort_config=args.sort_cfg)
+    w = workload(args.workload)
+    t_gen = time.perf_counter()
+    d_full, seps = w.device_text(local_rank)          # every rank generates the genome in its own HBM (milliseconds)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    n = int(d_full.numel())
+    n_bases = n - len(seps)
+    lo, hi = sh.slice(n)
+    d_slice = d_full[lo:hi].clone() if hi > lo else torch.zeros(1, dtype=torch.uint8, device=d_full.device)
+    if rank != 0 or args.no_verify:
+        del d_full
+        d_full = None
+    h_slice = torch.empty(max(hi - lo, 1), dtype=torch.uint8, pin_memory=True)
+    h_slice[:d_slice.numel()].copy_(d_slice)
+    n_words = (n + 31) // 32
+    h_out = torch.empty(n_words, dtype=torch.int64, pin_memory=True) if rank == 0 else None
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        sh.build(d_slice.data_ptr(), True, n, seps)
+    barrier()
+    l0 = binding.lib().debwt_launch_count()
+    dev_ms = sort_ms = sweep_ms = 0.0
+    sweeps = 0
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sh.build(d_slice.data_ptr(), True, n, seps)
+            st = sh.stats()
+            dev_ms += st["ms_total"]; sort_ms += st["ms_sort"]; sweep_ms += st["ms_sort_sweeps"]; sweeps += st["sort_sweeps"]
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    dev_ms /= args.steps
+    launches = int(binding.lib().debwt_launch_count() - l0)
+    clocks = clk.summary()
+    last = sh.stats()
+
+    def step_e2e():
+        sh.build(h_slice.data_ptr(), False, n, seps)
+        return sh.result_into(h_out.data_ptr()) if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sd = step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    tt = torch.tensor([dev_ms, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = (float(x) for x in tt.tolist())
+    keys_local = torch.tensor([last["n_keys_local"]], device="cuda", dtype=torch.int64)
+    kl = [torch.zeros_like(keys_local) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(kl, keys_local)
+    else:
+        kl = [keys_local]
+    if rank == 0:
+        sha = hashlib.sha256(h_out.numpy().tobytes()).hexdigest()
+        want = expected_sha(w.name)
+        verify = {"bwt_sha256": sha, "sha_expected": want, "sha_ok": (sha == want) if want else None}
+        if not args.no_verify:
+            try:
+                sharp_np, dollar_np = sd
+                bad, vms = api.verify_bwt_device(sh.result_device_ptr(), n, sharp_np, int(dollar_np[0]), d_full.data_ptr(), device=local_rank)
+                verify.update({"lf_inversion_bad_rows": bad, "lf_inversion_ms": vms, "lf_inversion_ok": bad == 0,
+                               "how": "debwt_verify_bwt_device on rank 0: LF mapping of the stitched result, list ranking by pointer "
+                                      "jumping, every row's symbol compared with the input text"})
+            except Exception as e:  # noqa: BLE001
+                verify.update({"lf_inversion_ok": None, "lf_inversion_error": str(e)})
+        nk_loc = last["n_keys_local"]
+        line = {
+            "metric": METRIC, "value": n_bases / (dev_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic (generated in HBM on every rank in %.2f s)" % t_gen,
+            "config": common_config(w, world),
+            "timing": "CUDA events on each rank's library stream around its whole build (debwt_shard_stats.ms_total), mean over the "
+                      "steps, max over ranks; wall per step %.3f ms (max over ranks)" % wall_ms,
+            "exchange": {"path": "debwt_shard_* (csrc/shard.cu): bucketing kernel stores into the owners' CUDA-IPC mapped buffers over "
+                                 "NVLink; control data over a shared-memory communicator; no NCCL on the data path",
+                         "keys_per_gpu": [int(x.item()) for x in kl]},
+            "clocks": clocks,
+            "e2e": {"value": n_bases / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * n_words,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": roofline_block(nk_loc, sweeps // max(args.steps, 1), sweep_ms / max(sweeps, 1), sort_ms / args.steps, 0.0,
+                                       " on rank 0's key range"),
+            "sizes": {k: last[k] for k in ("n_symbols", "n_keys", "n_branch", "n_blue", "n_codes")},
+            "hbm": {"arena_bytes_rank0": last["arena_bytes"]},
+            "verify": verify,
+            "bwt_sha256": sha,
+        }
+        print(json.dumps(line), flush=True)
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -580,6 +704,8 @@ def main():
     ap.add_argument("--no-file-to-file", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks (to measure the sampler's own cost)")
     ap.add_argument("--profile-phases", action="store_true", help="sharded path: add rank 0's synchronised per-phase times")
+    ap.add_argument("--orchestrator", default="c", choices=["c", "python"],
+                    help="N > 1: the sharded build behind the C ABI (csrc/shard.cu) or the Python harness debwt_b200/dist.py")
     ap.add_argument("--sharded", action="store_true", help="use the sharded (multi-GPU) code path even at N=1")
     args = ap.parse_args()
     if args.no_clocks:
@@ -590,8 +716,10 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
-    if world > 1 or args.sharded:
-        ours_sharded(args, rank, world, local_rank)
+    if (world > 1 or args.sharded) and args.orchestrator == "python":
+        ours_sharded_python(args, rank, world, local_rank)
+    elif world > 1 or args.sharded:
+        ours_shard(args, rank, world, local_rank)
     else:
         ours(args, rank, world, local_rank)
 

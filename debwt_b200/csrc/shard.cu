@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <thread>
 #include <vector>
@@ -60,6 +61,15 @@ __global__ void or_store_kernel(u64* __restrict__ dst, const u64* __restrict__ s
     const u64 v = src[i];
     if (i == 0 || i + 1 == n) { if (v) atomicOr(reinterpret_cast<unsigned long long*>(dst + i), (unsigned long long)v); }
     else dst[i] = v;
+}
+
+// copies between ranks are done by the SMs (16-byte loads / stores through the peer mapping, over NVLink): a cudaMemcpy
+// between two processes' IPC-mapped buffers may be staged through the host
+__global__ void __launch_bounds__(512) peer_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, u64 n16,
+                                                       u8* __restrict__ dst_tail, const u8* __restrict__ src_tail, u32 tail) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
 template <typename T>
@@ -130,6 +140,24 @@ int allgather(debwt_shard* s, const T* mine, size_t count, T* all) {
 int sync_all(debwt_shard* s) {
     SCUDA(cudaStreamSynchronize(s->st));
     return barrier(s);
+}
+
+// dst (possibly another rank's memory) <- src (this rank's), both 8-byte aligned
+int peer_copy(debwt_shard* s, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) {      // 8-byte aligned only: plain words
+        SCUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s->st));
+        return 0;
+    }
+    const u64 n16 = bytes / 16;
+    const u32 tail = (u32)(bytes % 16);
+    unsigned grid = (unsigned)std::min<u64>((n16 + 511) / 512, 148ull * 8);
+    if (grid == 0) grid = 1;
+    peer_copy_kernel<<<grid, 512, 0, s->st>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), n16,
+                                              static_cast<u8*>(dst) + n16 * 16, static_cast<const u8*>(src) + n16 * 16, tail);
+    DEBWT_COUNT(1);
+    SCUDA(cudaGetLastError());
+    return 0;
 }
 
 void unmap(debwt_shard* s, SharedBuf& b) {
@@ -231,9 +259,27 @@ int exchange_by_splitters(debwt_shard* s, const u64* items, u64 n_items, const u
     return 0;
 }
 
+struct PhaseClock {                                    // DEBWT_SHARD_PROFILE=1: synchronised per-phase wall times on stderr (rank 0)
+    bool on;
+    cudaStream_t st;
+    double t;
+    std::string out;
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    void tick(const char* name) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double n = now();
+        char b[64];
+        snprintf(b, sizeof b, " %s %.1f", name, (n - t) * 1e3);
+        out += b;
+        t = n;
+    }
+};
+
 int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64 N, const u64* seps, u64 R) {
     const int G = s->world, me = s->rank;
     cudaStream_t st = s->st;
+    PhaseClock pc{getenv("DEBWT_SHARD_PROFILE") != nullptr, st, PhaseClock::now(), ""};
     DevPool& pool = s->pool;
     SCUDA(cudaSetDevice(s->device));
     if (R == 0) SFAIL("no records");
@@ -284,7 +330,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         SCUDA(cudaMemsetAsync(W + wtot, 0, 16, st));
         for (int p = 0; p < G; ++p)
             if (p != me)
-                SCUDA(cudaMemcpyAsync(static_cast<u64*>(s->words.ptr[p]) + (u64)me * wp, W + (u64)me * wp, wp * 8, cudaMemcpyDeviceToDevice, st));
+                if (peer_copy(s, static_cast<u64*>(s->words.ptr[p]) + (u64)me * wp, W + (u64)me * wp, wp * 8)) return -1;
         u32 h_err[4] = {0, 0, 0, 0}, all_err[kMaxRanks * 4];
         SCUDA(cudaMemcpyAsync(h_err, d_err, 16, cudaMemcpyDeviceToHost, st));
         if (sync_all(s)) return -1;
@@ -297,6 +343,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         }
         if (nsep != R) SFAIL("input contains '#' or '$' inside a record (they are reserved for the record separators)");
     }
+    pc.tick("pack+gather");
     SCUDA(cudaEventRecord(s->ev[1], st));
 
     // ---- 2. keys of own slice, sampled splitters ----
@@ -329,6 +376,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
             h_split[i - 1] = valid.empty() ? kKmerMask : (valid[(size_t)i * valid.size() / G] & kKmerMask);   // k-mer boundaries
         SCUDA(cudaMemcpyAsync(d_split, h_split, kMaxRanks * 8, cudaMemcpyHostToDevice, st));
 
+        pc.tick("extract+splitters");
         // ---- 3. one exchange: every key goes to the owner of its k-mer ----
         if (exchange_by_splitters(s, keys, cnt, d_split, false, s->recv_a, d_small, &n_loc, n_all)) return -1;
         pool.rewind(mark);
@@ -338,6 +386,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
     if (total != NK) SFAIL("internal: key exchange lost keys");
     if (n_loc >= (1ull << 32) - (1u << 16)) SFAIL("a rank owns 2^32 keys or more: use more GPUs");
     S.n_keys_local = n_loc;
+    pc.tick("key_exchange");
     SCUDA(cudaEventRecord(s->ev[2], st));
 
     // ---- 4. sort the owned key range ----
@@ -356,6 +405,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         pool.adopt(sortws, sort_workspace_bytes(n_loc, s->sort_cfg));
     }
     SCUDA(cudaEventRecord(s->ev[3], st));
+    pc.tick("sort");
 
     // ---- 5. branch k-mer detection on the owned range ----
     KeyIndex ki;
@@ -368,10 +418,13 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         const auto mark = pool.mark();
         u64* q = nullptr;
         if (dalloc(s, &q, n_loc + 2)) return -1;
+        pc.tick("index");
         if (k_out_edges_queries(sk, n_loc, gmask, q, st)) return -1;
+        pc.tick("out_edges");
         u64 m_q = 0;                                   // duplicates (marked ~0) are dropped on the way, also on one rank
         if (exchange_by_splitters(s, q, n_loc, d_split, true, s->recv_b, d_small, &m_q, nullptr)) return -1;
         const u64* qr = static_cast<const u64*>(s->recv_b.ptr[me]);
+        pc.tick("query_exchange");
         if (n_loc) {
             if (k_apply_in_queries(sk, n_loc, ki, gmask, qr, m_q, st)) return -1;
             if (k_mark_heads_tails(W, d_seps, R, sk, n_loc, ki, gmask, st)) return -1;
@@ -379,6 +432,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         }
         SCUDA(cudaStreamSynchronize(st));
         pool.rewind(mark);
+        pc.tick("apply+propagate");
     }
     BranchTable bt;
     u64 b_base[kMaxRanks + 1] = {}, m_all[kMaxRanks] = {}, B_tot = 0, M_tot = 0;
@@ -410,7 +464,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
     if (ensure_shared(s, s->gkmer, (B_tot + 2) * 8)) return -1;
     for (int p = 0; p < G; ++p)
         if (bt.n_branch)
-            SCUDA(cudaMemcpyAsync(static_cast<u64*>(s->gkmer.ptr[p]) + b_base[me], bt.kmer, bt.n_branch * 8, cudaMemcpyDeviceToDevice, st));
+            if (peer_copy(s, static_cast<u64*>(s->gkmer.ptr[p]) + b_base[me], bt.kmer, bt.n_branch * 8)) return -1;
     if (sync_all(s)) return -1;
     BranchTable gbt;
     gbt.n_branch = B_tot; gbt.kmer = static_cast<u64*>(s->gkmer.ptr[me]);
@@ -422,6 +476,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         if (k_branch_index(gbt, st)) return -1;
     }
     S.n_branch = B_tot; S.n_blue = M_tot;
+    pc.tick("branch_table");
     SCUDA(cudaEventRecord(s->ev[4], st));
 
     // ---- 6. sentinel-window suffixes: ranked on every rank (same text), insertion points summed over the key ranges ----
@@ -443,7 +498,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
             if (dalloc(s, &d_loc, nspec)) return -1;
             SCUDA(cudaMemcpyAsync(d_loc, loc.data(), nspec * 8, cudaMemcpyHostToDevice, st));
             for (int p = 0; p < G; ++p)
-                SCUDA(cudaMemcpyAsync(static_cast<u64*>(s->mail.ptr[p]) + (u64)me * nspec, d_loc, nspec * 8, cudaMemcpyDeviceToDevice, st));
+                if (peer_copy(s, static_cast<u64*>(s->mail.ptr[p]) + (u64)me * nspec, d_loc, nspec * 8)) return -1;
             if (sync_all(s)) return -1;
             std::vector<u64> all((size_t)G * nspec);
             SCUDA(cudaMemcpyAsync(all.data(), s->mail.ptr[me], all.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -468,6 +523,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
     SCUDA(cudaMemcpyAsync(d_emit, h_emit_pos.data(), h_emit_pos.size() * 8, cudaMemcpyHostToDevice, st));
     SCUDA(cudaMemcpyAsync(d_tail, h_tail_pos.data(), R * 8, cudaMemcpyHostToDevice, st));
 
+    pc.tick("special");
     // ---- 7. branch codes of own position slice at global code indices ----
     u32 *mo = nullptr, *wpfx = nullptr;
     u64 *rec_entry = nullptr, *rec_index = nullptr;
@@ -527,6 +583,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
     SCUDA(cudaMemcpyAsync(&dollar_index, tail_idx + (R - 1), 8, cudaMemcpyDeviceToHost, st));
     if (k_fix_records(rec_entry, m_rec, mo, wpfx, pos_lo, code_base, st)) return -1;
     SCUDA(cudaStreamSynchronize(st));
+    pc.tick("codes");
     SCUDA(cudaEventRecord(s->ev[7], st));
 
     // ---- 8. blue entries travel to the owner of their k-mer ----
@@ -565,8 +622,8 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
                 u64 off = 0;
                 for (int src = 0; src < me; ++src) off += mat[src * kMaxRanks + d];
                 u64* base = static_cast<u64*>(s->recv_b.ptr[d]);
-                SCUDA(cudaMemcpyAsync(base + off, e_part + curs[d], counts[d] * 8, cudaMemcpyDeviceToDevice, st));
-                SCUDA(cudaMemcpyAsync(base + m_all[d] + 2 + off, i_part + curs[d], counts[d] * 8, cudaMemcpyDeviceToDevice, st));
+                if (peer_copy(s, base + off, e_part + curs[d], counts[d] * 8)) return -1;
+                if (peer_copy(s, base + m_all[d] + 2 + off, i_part + curs[d], counts[d] * 8)) return -1;
             }
             if (sync_all(s)) return -1;
             e_recv = static_cast<const u64*>(s->recv_b.ptr[me]);
@@ -575,6 +632,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
             SFAIL("internal: blue entry count mismatch");
         }
         if (G > 1) pool.rewind(mark_records);          // the flagged records are dead once they have been sent (one rank reads them in place)
+        pc.tick("blue_exchange");
         if (dalloc(s, &blue, bt.n_blue + 1)) return -1;
         SCUDA(cudaMemsetAsync(bt.cursor, 0, (bt.n_branch + 1) * 4, st));
         if (k_scatter_blue(e_recv, i_recv, bt.n_blue, bt, blue, st)) return -1;
@@ -585,6 +643,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         if (k_sort_blue(blue, bt, spv, d_work, st)) { s->err = debwt_last_error(); return -1; }
     }
 
+    pc.tick("scatter+k10");
     // ---- 9. every rank emits its own contiguous run of BWT rows and stores it into rank 0's result ----
     const u64 n_out = (N + 31) / 32;
     u64 r_lo_all[kMaxRanks + 1];
@@ -642,7 +701,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         if (tot != R - 1) SFAIL("internal: wrong number of '#' rows");
         if (G > 1) {
             if (ensure_shared(s, s->mail, (R + 2) * 8)) return -1;
-            if (scnt) SCUDA(cudaMemcpyAsync(static_cast<u64*>(s->mail.ptr[0]) + off, d_sharp, scnt * 8, cudaMemcpyDeviceToDevice, st));
+            if (scnt && peer_copy(s, static_cast<u64*>(s->mail.ptr[0]) + off, d_sharp, scnt * 8)) return -1;
             if (sync_all(s)) return -1;
             if (me == 0) {
                 s->sharp.resize(tot);
@@ -655,6 +714,8 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         }
         std::sort(s->sharp.begin(), s->sharp.end());
     }
+    pc.tick("emit+stitch");
+    if (pc.on && me == 0) fprintf(stderr, "[shard phases ms]%s\n", pc.out.c_str());
     float ms = 0;
     SCUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1])); S.ms_total = ms;
     SCUDA(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3])); S.ms_sort = ms;
@@ -678,6 +739,11 @@ int debwt_shard_create(debwt_shard** out, int device, int rank, int world, const
     auto fail = [&](const std::string& m) { set_error(m); delete s; return -1; };
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return fail("cannot create a stream");
+    {   // K10 takes its work lists from the stream-ordered pool: keep what it frees cached instead of returning it to the driver
+        cudaMemPool_t mp;
+        unsigned long long thr = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
     for (auto& e : s->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail("cannot create an event");
     s->pool.st = s->st;
     std::string err;
