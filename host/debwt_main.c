@@ -39,7 +39,7 @@ static void usage(void) {
     fprintf(stderr, "-t (optional): accepted for compatibility (the build runs on the GPU)\n");
     fprintf(stderr, "-k (optional): k-mer length (from 12 to 32, default 32)\n");
     fprintf(stderr, "-j (optional): accepted for compatibility, ignored (no Jellyfish needed)\n");
-    fprintf(stderr, "-g (optional): CUDA device ordinal (default 0)\n");
+    fprintf(stderr, "-g (optional): CUDA device ordinal (default 0), or a comma-separated list (e.g. 0,1,2,3): the build is sharded over those GPUs\n");
     fprintf(stderr, "-n (optional): seed; IUPAC ambiguity codes are replaced by a pseudo-random compatible base (what otherTool/transferN does, reproducibly)\n");
     fprintf(stderr, "reference: sequence in fasta or fastq format (plain or gzip)\n");
 }
@@ -85,6 +85,7 @@ typedef struct {
     char* park;
     uint64_t park_n, park_cap;
     int dry;                   /* no device: only the input checks run */
+    int collect;               /* several GPUs: the whole text is collected in host memory, every GPU uploads its slice */
     int resolve;               /* -n: IUPAC policy */
     unsigned long long amb_seed;
 } sink_t;
@@ -111,7 +112,7 @@ static int sink_room(sink_t* s) {
 static int sink_put(sink_t* s, const unsigned char* p, uint64_t n) {
     if (s->dry) { s->n += n; return 0; }
     if (!s->ctx) {
-        if (s->job->done) {
+        if (!s->collect && s->job->done) {
             if (sink_attach(s)) { s->failed = 1; return 2; }
             return sink_put(s, p, n);
         }
@@ -163,14 +164,25 @@ int main(int argc, char* argv[]) {
     if (argc < 4 || (argc & 1) == 1) { usage(); return 1; }
     const char* source = argv[argc - 1];
     const char* obj = NULL;
-    int k = 32, gpu = 0, resolve = 0;
+    int k = 32, gpu = 0, resolve = 0, ngpu = 1;
+    int gpus[16] = {0};
     unsigned long long amb_seed = 0;
     for (int i = 1; i < argc - 1; i += 2) {
         if (strcmp(argv[i], "-o") == 0) obj = argv[i + 1];
         else if (strcmp(argv[i], "-t") == 0) {
             if (atoi(argv[i + 1]) == 0) { fprintf(stderr, "thread number must be a number!\n"); return 1; }
         } else if (strcmp(argv[i], "-j") == 0) { /* ignored */
-        } else if (strcmp(argv[i], "-g") == 0) gpu = atoi(argv[i + 1]);
+        } else if (strcmp(argv[i], "-g") == 0) {
+            const char* q = argv[i + 1];
+            ngpu = 0;
+            while (*q && ngpu < 16) {
+                gpus[ngpu++] = atoi(q);
+                while (*q && *q != ',') q++;
+                if (*q == ',') q++;
+            }
+            if (ngpu == 0) { usage(); return 1; }
+            gpu = gpus[0];
+        }
         else if (strcmp(argv[i], "-n") == 0) { resolve = 1; amb_seed = strtoull(argv[i + 1], NULL, 10); }
         else if (strcmp(argv[i], "-k") == 0) {
             k = atoi(argv[i + 1]);
@@ -184,6 +196,47 @@ int main(int argc, char* argv[]) {
     remove(obj);
 
     double t0 = now_s();
+    if (ngpu > 1) {
+        /* ---- several GPUs: debwt_build_multi, one thread per GPU, each uploads its own position slice ---- */
+        if (resolve) { fprintf(stderr, "-n is not available with several GPUs\n"); return 1; }
+        fastx_t* fxm = fastx_open(source);
+        if (!fxm) { fprintf(stderr, "can not open ref file\n"); return 1; }
+        sink_t m;
+        memset(&m, 0, sizeof m);
+        m.collect = 1;
+        int mrc = fastx_stream(fxm, on_bases, on_record, &m);
+        fastx_close(fxm);
+        if (mrc == 3) return 1;
+        if (mrc < 0) { fprintf(stderr, "malformed input file\n"); return 1; }
+        if (m.failed) return 1;
+        if (m.nrec == 0) { fprintf(stderr, "no sequence found in %s\n", source); return 1; }
+        { const unsigned char c = '$'; if (sink_put(&m, &c, 1)) return 1; }
+        double t1m = now_s();
+        const uint64_t nwords = (m.n + 31) / 32, nsharp = m.nrec - 1;
+        uint64_t* bwt = (uint64_t*)malloc((nwords ? nwords : 1) * 8);
+        uint64_t* sharp = (uint64_t*)malloc((nsharp ? nsharp : 1) * 8);
+        uint64_t dollar = 0;
+        debwt_shard_stats ss;
+        if (!bwt || !sharp) { fprintf(stderr, "out of host memory\n"); return 1; }
+        if (debwt_build_multi(gpus, ngpu, m.park, m.n, m.seps, m.nrec, bwt, sharp, &dollar, &ss)) {
+            fprintf(stderr, "deBWT: %s\n", debwt_last_error());
+            return 1;
+        }
+        double t2m = now_s();
+        size_t olm = strlen(obj);
+        char* pm = (char*)malloc(olm + 3);
+        memcpy(pm, obj, olm);
+        pm[olm] = '.'; pm[olm + 2] = 0;
+        if (write_file(obj, bwt, nwords * 8)) return 1;
+        pm[olm + 1] = '#';
+        if (write_file(pm, sharp, nsharp * 8)) return 1;
+        pm[olm + 1] = '$';
+        if (write_file(pm, &dollar, 8)) return 1;
+        fprintf(stderr, "BWTLEN=%llu (%llu records), read %.3f s; %d GPUs: upload + build + download %.3f s (rank 0 device %.1f ms, sort %.1f ms); write %.3f s\n",
+                (unsigned long long)m.n, (unsigned long long)m.nrec, t1m - t0, ngpu, t2m - t1m, ss.ms_total, ss.ms_sort, now_s() - t2m);
+        fflush(NULL);
+        _exit(0);
+    }
     setenv("CUDA_MODULE_LOADING", "EAGER", 0);          /* kernel images load with the context, on the second thread */
     create_job job;
     memset(&job, 0, sizeof job);

@@ -106,3 +106,23 @@ def test_cli_writes_reference_files(name, tmp_path):
     assert out.read_bytes().hex() == case["bwt"]
     assert (tmp_path / "out.bwt.#").read_bytes().hex() == case["sharp"]
     assert (tmp_path / "out.bwt.$").read_bytes().hex() == case["dollar"]
+
+
+@pytest.mark.gpu
+def test_cli_multi_gpu_list(tmp_path):
+    """deBWT -g a,b,...: the sharded build behind the C ABI (debwt_build_multi); two ranks share cuda:0 when the box has one GPU"""
+    import torch
+    exe = os.path.join(ROOT, "host", "deBWT")
+    case = G["small"]["haplotypes_6x1500"]
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for i, r in enumerate(case["records"]):
+            f.write(f">r{i}\n{r}\n")
+    out1, out2 = tmp_path / "one.bwt", tmp_path / "multi.bwt"
+    assert subprocess.run([exe, "-o", str(out1), str(fa)], capture_output=True, text=True).returncode == 0
+    devs = ",".join(str(d) for d in range(min(torch.cuda.device_count(), 4))) if torch.cuda.device_count() > 1 else "0,0,0"
+    r = subprocess.run([exe, "-o", str(out2), "-g", devs, str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for ext in ("", ".#", ".$"):
+        assert open(str(out1) + ext, "rb").read() == open(str(out2) + ext, "rb").read(), ext
+    assert open(out1, "rb").read().hex() == case["bwt"]
