@@ -44,11 +44,13 @@ def join_records(records: Sequence) -> tuple[np.ndarray, np.ndarray]:
 class BwtBuilder:
     """One context == one GPU (replaces the reference's process-wide state)."""
 
-    def __init__(self, device: int = 0, sort_config: int = 0):
+    def __init__(self, device: int = 0, sort_config: int = 0, blue_grouping: int = 0):
         self._h = c_p()
         check(lib().debwt_create(ctypes.byref(self._h), device))
         if sort_config:
             lib().debwt_set_sort_config(self._h, sort_config)
+        if blue_grouping:
+            lib().debwt_set_blue_grouping(self._h, blue_grouping)
         self._keep = None
 
     def close(self):

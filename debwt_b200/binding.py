@@ -48,6 +48,7 @@ _SIGS = {
     "debwt_create": (ctypes.c_int, [ctypes.POINTER(c_p), ctypes.c_int]),
     "debwt_destroy": (None, [c_p]),
     "debwt_set_sort_config": (ctypes.c_int, [c_p, ctypes.c_int]),
+    "debwt_set_blue_grouping": (ctypes.c_int, [c_p, ctypes.c_int]),
     "debwt_set_ambiguity_policy": (ctypes.c_int, [c_p, ctypes.c_int, c_u64]),
     "debwt_set_records": (ctypes.c_int, [c_p, ctypes.POINTER(c_p), ctypes.POINTER(c_u64), c_u64]),
     "debwt_set_text": (ctypes.c_int, [c_p, c_p, c_u64, c_p, c_u64]),

@@ -218,6 +218,12 @@ int debwt_set_sort_config(debwt_ctx* c, int cfg) {
     return old;
 }
 
+int debwt_set_blue_grouping(debwt_ctx* c, int mode) {
+    int old = c->blue_grouping;
+    c->blue_grouping = mode >= 0 && mode <= 2 ? mode : 0;
+    return old;
+}
+
 int debwt_set_ambiguity_policy(debwt_ctx* c, int resolve, uint64_t seed) {
     if (!c) FAIL("null context");
     c->resolve_ambiguous = resolve != 0;
@@ -435,16 +441,35 @@ int debwt_build(debwt_ctx* c, int k) {
     u32 *d_mo = nullptr, *d_wp = nullptr;
     u64* d_blue = nullptr;
     void* d_scanws = nullptr;
-    if (dalloc(pool, &d_mo, nbw + 2) || dalloc(pool, &d_wp, nbw + 2) || dalloc(pool, &d_blue, bt.n_blue + 1) ||
-        pool.alloc(&d_scanws, scan_workspace_bytes(nbw)))
+    // blue entries into their segments: by a cursor per segment, or appended densely and grouped by a radix sort on the
+    // branch id (the id sits at the top of the key, so ceil(bits / 8) passes do it)
+    int id_bits = 1;
+    while (id_bits < 64 && (bt.n_branch >> id_bits)) ++id_bits;
+    const bool group_by_sort = id_bits <= 28 && n < (1ull << 32) && bt.n_blue > 1 &&
+                               (c->blue_grouping == 2 || (c->blue_grouping == 0 && bt.n_blue >= (1ull << 20)));
+    const int id_shift = 64 - id_bits;
+    u64 *d_bka = nullptr, *d_bkb = nullptr, *d_bcount = nullptr;
+    void* d_bsortws = nullptr;
+    const int bcfg = kDefaultSortCfg;
+    if (dalloc(pool, &d_mo, nbw + 2) || dalloc(pool, &d_wp, nbw + 2) || pool.alloc(&d_scanws, scan_workspace_bytes(nbw)))
         return -1;
+    if (group_by_sort) {
+        if (dalloc(pool, &d_bka, bt.n_blue + 2) || dalloc(pool, &d_bkb, bt.n_blue + 2) || dalloc(pool, &d_bcount, 2) ||
+            pool.alloc(&d_bsortws, sort_workspace_bytes(bt.n_blue, bcfg)))
+            return -1;
+        CUDA_TRY(cudaMemsetAsync(d_bcount, 0, 16, st));
+    } else if (dalloc(pool, &d_blue, bt.n_blue + 1)) return -1;
     CUDA_TRY(cudaMemsetAsync(d_mo, 0, (nbw + 2) * 4, st));
-    if (k_flag_positions(d_text, n, d_seps, R, bt, d_mo, d_blue, st)) return -1;
+    if (group_by_sort) {
+        if (k_flag_positions_keys(d_text, n, d_seps, R, bt, id_shift, d_mo, d_bka, d_bcount, st)) return -1;
+    } else if (k_flag_positions(d_text, n, d_seps, R, bt, d_mo, d_blue, st)) return -1;
     if (k_patch_bits(d_mo, d_emit, h_emit_pos.size(), st)) return -1;
     if (scan_exclusive_u32(d_mo, d_wp, nbw, true, d_scanws, d_tot, st)) return -1;
-    u64 n_codes = 0;
+    u64 n_codes = 0, n_appended = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_codes, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    if (group_by_sort) CUDA_TRY(cudaMemcpyAsync(&n_appended, d_bcount, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (group_by_sort && n_appended != bt.n_blue) FAIL("internal: multi-in positions found in the text do not match the k-mer counts");
     S.n_codes = n_codes;
     const u64 ncw = n_codes / 32 + 3;
     u64* d_codes = nullptr; u32* d_sep = nullptr;
@@ -453,7 +478,16 @@ int debwt_build(debwt_ctx* c, int k) {
     CUDA_TRY(cudaMemsetAsync(d_sep, 0, (ncw + 1) * 4, st));
     if (k_emit_codes(d_text, n, d_mo, d_wp, d_codes, st)) return -1;
     if (k_mark_sep_codes(d_mo, d_wp, d_tail, R, d_sep, d_tail_idx, st)) return -1;
-    if (k_blue_fix(d_blue, bt.n_blue, d_mo, d_wp, st)) return -1;
+    if (group_by_sort) {
+        if (k_blue_keys_fix(d_bka, bt.n_blue, d_mo, d_wp, st)) return -1;
+        SortWorkspace bws;
+        sort_workspace_bind(bws, d_bsortws, bt.n_blue, bcfg);
+        bws.first_pass = id_shift / 8;
+        if (radix_sort_u64(d_bka, d_bkb, bt.n_blue, bws, st, &d_blue)) return -1;
+        if (k_blue_keys_strip(d_blue, bt.n_blue, st)) return -1;
+        pool.adopt(d_blue == d_bka ? d_bkb : d_bka, (bt.n_blue + 2) * 8);
+        pool.adopt(d_bsortws, sort_workspace_bytes(bt.n_blue, bcfg));
+    } else if (k_blue_fix(d_blue, bt.n_blue, d_mo, d_wp, st)) return -1;
     u64 dollar_index = 0;
     CUDA_TRY(cudaMemcpyAsync(&dollar_index, d_tail_idx + (R - 1), 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

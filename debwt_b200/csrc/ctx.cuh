@@ -82,6 +82,7 @@ struct DevPool {
 struct debwt_ctx {
     int device = 0;
     int sort_cfg = debwt::kDefaultSortCfg;
+    int blue_grouping = 0;              // K9: 0 auto, 1 per-segment cursors, 2 grouping sort (debwt_set_blue_grouping)
     cudaStream_t st = nullptr;
     debwt::DevPool pool;
     // input

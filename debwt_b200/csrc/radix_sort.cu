@@ -387,7 +387,7 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
     u64 *src = a, *dst = b;
     int sweeps = 0;
     if (ws.ev_sweep_begin) CUDA_TRY(cudaEventRecord(ws.ev_sweep_begin, st));
-    for (int p = 0; p < PASSES; ++p) {
+    for (int p = ws.first_pass; p < PASSES; ++p) {
         if (skip[p]) continue;
         int rc;
         if (ws.cfg >= TMA_CFG_BASE) rc = launch_tma_sweep(ws.cfg, src, dst, n, p, ws, st);

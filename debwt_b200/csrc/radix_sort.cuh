@@ -19,6 +19,9 @@ struct SortWorkspace {
     u32* key_index = nullptr;
     int key_index_bits = 0;
     bool* key_index_done = nullptr;
+    // only the passes >= first_pass run (the caller knows the low 8 * first_pass bits need no ordering, e.g. K9's
+    // (branch id, position) keys, which only have to be grouped by branch id)
+    int first_pass = 0;
 };
 
 int sort_config_tile(int cfg);

@@ -869,6 +869,91 @@ __global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restri
     }
 }
 
+// K9 with the blue entries grouped by a sort instead of per-segment cursors: every multi-in position appends one key
+//   (branch id << shift) | (position << 4) | 8 | prev          (shift >= 36; the branch id ends at bit 63)
+// to a dense array -- one atomic per 4096-position block, coalesced stores -- and the radix passes over the bits from
+// `shift` up group the keys by branch id, i.e. into their segments (the order inside a segment is K10's business).
+// Replaces 517 M cursor atomics and scattered 8-byte stores at 3.1 Gbp.  Needs N < 2^32 and at most 2^28 branch k-mers.
+__global__ void __launch_bounds__(TPB) flag_positions_keys_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
+                                                                 const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
+                                                                 int shift, u32* __restrict__ mo_bits, u64* __restrict__ bkeys,
+                                                                 unsigned long long* __restrict__ counter) {
+    __shared__ TileText t;
+    __shared__ u32 s_cnt[TILE_ROWS][TPB / 32];
+    __shared__ u64 s_base;
+    const u64 base = (u64)blockIdx.x * TILE_POS;
+    tile_load(t, words, nwords_total, base, n, seps, n_rec);
+    const bool one_record = t.rec_first == t.rec_last;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 key[TILE_ROWS];
+#pragma unroll
+    for (int j = 0; j < TILE_ROWS; ++j) {
+        const u32 local = j * TPB + threadIdx.x;
+        const u64 p = base + local;
+        bool mo = false;
+        key[j] = 0;
+        if (p < n) {
+            u64 r = t.rec_first, sep = t.sep_first, start = t.start_first;
+            bool in_text = true;
+            if (!one_record) {
+                r = record_of(seps, n_rec, p);
+                in_text = r < n_rec;
+                if (in_text) { sep = seps[r]; start = r ? seps[r - 1] + 1 : 0; }
+            }
+            if (in_text && p + KMER <= sep) {
+                const u64 x = tile_window(t, local) & ~3ull;
+                u64 b;
+                if (branch_lookup(bt, x, b)) {
+                    const u32 f = (u32)(bt.kmer[b] & 3ull);
+                    mo = f & 1u;
+                    if (f & 2u) {
+                        u32 prev;
+                        if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
+                        else prev = text_symbol(words, p - 1);
+                        key[j] = (b << shift) | (p << 4) | prev | 8ull;       // bit 3 marks "present" (b, p and prev may all be 0)
+                    }
+                }
+            }
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, mo);
+        if (lane == 0 && p < n + 32) mo_bits[p >> 5] = bal;
+        const u32 bmi = __ballot_sync(0xffffffffu, key[j] != 0);
+        if (lane == 0) s_cnt[j][warp] = __popc(bmi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                            // 128 partial counts: serial exclusive scan, one atomic for the block
+        u32 run = 0;
+        for (int j = 0; j < TILE_ROWS; ++j)
+            for (int w = 0; w < TPB / 32; ++w) { const u32 c = s_cnt[j][w]; s_cnt[j][w] = run; run += c; }
+        s_base = run ? atomicAdd(counter, (unsigned long long)run) : 0;
+    }
+    __syncthreads();
+    const u64 bb = s_base;
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < TILE_ROWS; ++j) {
+        const u32 bmi = __ballot_sync(0xffffffffu, key[j] != 0);
+        if (key[j]) bkeys[bb + s_cnt[j][warp] + __popc(bmi & lt)] = key[j];
+    }
+}
+
+// position -> spIndex inside the keys, in append order (positions nearly ascending: the bitmap and prefix reads are
+// sequential, where after the grouping they would be random)
+__global__ void __launch_bounds__(TPB) blue_keys_fix_kernel(u64* __restrict__ bkeys, u64 m, const u32* __restrict__ mo_bits,
+                                                           const u32* __restrict__ word_prefix) {
+    const u64 e = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (e >= m) return;
+    const u64 v = bkeys[e];
+    const u64 field = 0xFFFFFFFFull << 4;
+    bkeys[e] = (v & ~field) | (sp_index_of(mo_bits, word_prefix, (v >> 4) & 0xFFFFFFFFull) << 4);
+}
+
+// grouped keys -> blue entries (spIndex << 4) | prev, in place
+__global__ void __launch_bounds__(TPB) blue_keys_strip_kernel(u64* __restrict__ bkeys, u64 m) {
+    const u64 e = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (e < m) bkeys[e] &= 0xFFFFFFFF7ull;
+}
+
 __global__ void __launch_bounds__(TPB) patch_bits_kernel(u32* __restrict__ mo_bits, const u64* __restrict__ pos, u64 m) {
     const u64 t = (u64)blockIdx.x * TPB + threadIdx.x;
     if (t < m) atomicOr(mo_bits + (pos[t] >> 5), 1u << (pos[t] & 31));
@@ -923,6 +1008,31 @@ __global__ void __launch_bounds__(TPB) blue_fix_kernel(u64* __restrict__ blue, u
 int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, u32* mo_bits, u64* blue,
                      cudaStream_t st) {
     flag_positions_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, bt, mo_bits, blue);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_flag_positions_keys(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, int shift, u32* mo_bits,
+                          u64* bkeys, u64* d_counter, cudaStream_t st) {
+    flag_positions_keys_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, bt, shift, mo_bits, bkeys,
+                                                                      reinterpret_cast<unsigned long long*>(d_counter));
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_blue_keys_fix(u64* bkeys, u64 m, const u32* mo_bits, const u32* word_prefix, cudaStream_t st) {
+    if (m == 0) return 0;
+    blue_keys_fix_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(bkeys, m, mo_bits, word_prefix);
+    DEBWT_COUNT(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_blue_keys_strip(u64* bkeys, u64 m, cudaStream_t st) {
+    if (m == 0) return 0;
+    blue_keys_strip_kernel<<<grid_for(m, TPB), TPB, 0, st>>>(bkeys, m);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -95,6 +95,14 @@ int k_special_insertion(const u64* sorted, u64 n, KeyIndex ki, const u64* pads, 
 // mo_bits: ceil(n/32)+1 u32 words; blue: M u64 entries (position << 4 | prev)
 int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, u32* mo_bits, u64* blue,
                      cudaStream_t st);
+// the same with the blue entries appended as (branch id << shift | position << 4 | 8 | prev) keys to a dense array
+// (*d_counter, zeroed, ends up as their number).  k_blue_keys_fix turns the positions into spIndex while the keys are still
+// in append order, a radix sort on the bits from `shift` up groups them into their segments, k_blue_keys_strip leaves the
+// blue entries (spIndex << 4) | prev.  Needs N < 2^32, shift >= 36.
+int k_flag_positions_keys(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, int shift, u32* mo_bits,
+                          u64* bkeys, u64* d_counter, cudaStream_t st);
+int k_blue_keys_fix(u64* bkeys, u64 m, const u32* mo_bits, const u32* word_prefix, cudaStream_t st);
+int k_blue_keys_strip(u64* bkeys, u64 m, cudaStream_t st);
 int k_patch_bits(u32* mo_bits, const u64* positions, u64 m, cudaStream_t st);
 // sp_codes: ceil(S/32)+3 u64 zeroed; codes packed 32 per word, code j at bits 2*(31-(j&31))
 int k_emit_codes(const u64* words, u64 n, const u32* mo_bits, const u32* word_prefix, u64* sp_codes, cudaStream_t st);

@@ -66,6 +66,10 @@ int debwt_create(debwt_ctx** out, int device);
 void debwt_destroy(debwt_ctx* ctx);
 /* tuning knob for the sort kernel configuration (0 = default); returns the previous value */
 int debwt_set_sort_config(debwt_ctx* ctx, int cfg);
+/* how K9 brings the blue entries (src/generateSP.c:584-605) into their segments: 1 = one cursor per segment (atomics +
+   scattered stores), 2 = dense append + radix sort on the branch id, 0 (default) = 2 when there are >= 2^20 entries.
+   Same output either way; returns the previous value */
+int debwt_set_blue_grouping(debwt_ctx* ctx, int mode);
 
 /* What to do with symbols other than A, C, G, T.  resolve = 0 (default): the build fails, like the reference asks of its
    input ("make sure your sequence don't contain any uncertain characters like 'N'", src/main.c:178).  resolve = 1: IUPAC

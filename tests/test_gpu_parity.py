@@ -218,6 +218,40 @@ def test_bwt_huge_segments_vs_oracle(copies, el_len, muts):
     assert all((a == b_).all() for a, b_ in zip(want, got))
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", ["golden_small", "large_segments", "many_records", "c4_like"])
+def test_blue_grouping_modes(name, mode):
+    # K9's two ways of bringing the blue entries into their segments (per-segment cursors / dense append + radix sort on
+    # the branch id; debwt_set_blue_grouping) give the oracle's BWT
+    if name == "golden_small":
+        cases = [G["small"][k]["records"] for k in sorted(G["small"])]
+    elif name == "large_segments":
+        rng = np.random.default_rng(15)
+        master = synth.random_bases(78, 2500)
+        parts = []
+        for c in range(700):
+            el = master.copy()
+            idx = rng.integers(0, el.size, size=20)
+            el[idx] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=20)]
+            parts.append(el)
+        cases = [[np.concatenate(parts[:300]), np.concatenate(parts[300:])]]
+    elif name == "many_records":
+        rng = random.Random(99)
+        base = rnd(rng, 80)
+        cases = [[base[:rng.randint(33, 80)] if i % 2 else rnd(rng, rng.randint(33, 90)) for i in range(300)]]
+    else:
+        base = synth.config2(200_000, 4_000, 3, 0.1)[0]
+        cases = [[base] + [synth._mutate(base, 5 + i, 0.001) for i in range(4)]]
+    for recs in cases:
+        sym, _ = st.text_from_records(as_bytes_records(recs) if not isinstance(recs[0], str) else recs)
+        want = coracle.bwt(sym)
+        with api.BwtBuilder(blue_grouping=mode) as b:
+            b.set_records(recs)
+            b.build()
+            got = b.result()
+        assert all((a == b_).all() for a, b_ in zip(want, got))
+
+
 def test_bwt_errors():
     with pytest.raises(DebwtError):
         api.build_bwt(["ACGT" * 8])                 # 32 bp: "Length <= 32!" (src/collect#$.c:41-45)
