@@ -349,7 +349,7 @@ def ours(args, rank, world, local_rank):
     h_out = torch.empty(n_words, dtype=torch.int64, pin_memory=True)
     torch.cuda.synchronize()
 
-    b = api.BwtBuilder(device=local_rank, sort_config=args.sort_cfg)
+    b = api.BwtBuilder(device=local_rank, sort_config=args.sort_cfg, blue_grouping=int(os.environ.get("DEBWT_BLUE", "0")))
 
     def step_resident():
         b.set_text_device(d_text.data_ptr(), n, seps)

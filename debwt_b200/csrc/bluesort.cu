@@ -35,7 +35,8 @@ constexpr int MID_SEG = 128;
 constexpr int BIG_TPB = 512;
 constexpr int SMEM_SEG = 4096;     // == CHUNK: largest segment sorted entirely in shared memory
 
-__device__ __forceinline__ u32 fetch_sep(const u32* __restrict__ sep, u64 s) {
+__device__ __forceinline__ u32 fetch_sep(const SpView& v, u64 s) {
+    const u32* __restrict__ sep = v.sep;
     const u64 i = s >> 5;
     const u32 sh = (u32)(s & 31);
     const u32 lo = sep[i];
@@ -49,7 +50,7 @@ __device__ __forceinline__ bool sp_less_from(const SpView& v, u64 sa, u64 sb, u3
     sb += skip;
     for (;;) {
         const u64 ca = text_window32(v.codes, sa), cb = text_window32(v.codes, sb);
-        const u32 fa = fetch_sep(v.sep, sa), fb = fetch_sep(v.sep, sb);
+        const u32 fa = fetch_sep(v, sa), fb = fetch_sep(v, sb);
         if ((fa | fb) == 0) {
             if (ca != cb) return ca < cb;
         } else {
@@ -75,7 +76,7 @@ __device__ __forceinline__ Cached cache_of(const SpView& v, u64 entry) {
     const u64 s = entry >> 4;
     Cached c;
     c.word = text_window32(v.codes, s);
-    c.plain = fetch_sep(v.sep, s) == 0;
+    c.plain = fetch_sep(v, s) == 0;
     return c;
 }
 
@@ -306,6 +307,99 @@ __device__ void net_sort(const SegArrays& g, const SegArrays& s, u32 len, bool i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed network for items that sit in shared memory and hold no separator code: one u64 per entry =
+// (the next ADV codes of its string, left-aligned) | (its index in the item), so a compare-exchange moves 8 bytes
+// instead of an (entry, word) pair, all elements are distinct (the order is the stable one), and the entries are
+// permuted once at the end.  (A (word, 16-bit index) pair network that keeps all 32 codes was measured too: the second
+// array costs as many shared-memory instructions as it saves bytes -- no gain over the (entry, word) network.)
+// Two consecutive stages of the bitonic network always act on closed groups of four elements (mirror k + half cleaner
+// k/4; half cleaners 2j + j): a thread loads such a quad, does both stages in registers and stores it, which halves the
+// shared-memory traffic and the barriers again.
+// ---------------------------------------------------------------------------------------------
+constexpr int ilog2_ceil(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
+
+template <int CH>
+struct Packed {
+    static constexpr int IB = ilog2_ceil(CH);                          // index bits
+    static constexpr u32 ADV = (64 - IB) / 2;                          // codes compared per step: 27 (CH 512), 26 (CH 4096)
+    static constexpr u64 WMASK = ~((1ull << (64 - 2 * (int)ADV)) - 1ull);
+    static constexpr u64 IMASK = (1ull << IB) - 1ull;
+};
+
+__device__ __forceinline__ void cx64(u64& a, u64& b) {
+    if (b < a) { const u64 t = a; a = b; b = t; }
+}
+
+// elements beyond len are virtual +inf: never stored, and every compare-exchange moves the minimum down
+struct Quad {
+    u32 q[4];
+    u64 r[4];
+    __device__ __forceinline__ void load(const u64* a, u32 len) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) r[m] = q[m] < len ? a[q[m]] : ~0ull;
+    }
+    __device__ __forceinline__ void store(u64* a, u32 len) const {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) if (q[m] < len) a[q[m]] = r[m];
+    }
+};
+
+__device__ void packed_sort(u64* a, u32 len) {
+    const u32 P = pow2_at_least(len < 4 ? 4 : len);
+    const u32 nq = P >> 2;
+    // levels 2 and 4 on aligned quads: mirror 2, mirror 4, half cleaner 1
+    for (u32 t = threadIdx.x; t < nq; t += blockDim.x) {
+        Quad v;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) v.q[m] = 4 * t + m;
+        v.load(a, len);
+        cx64(v.r[0], v.r[1]); cx64(v.r[2], v.r[3]);
+        cx64(v.r[0], v.r[3]); cx64(v.r[1], v.r[2]);
+        cx64(v.r[0], v.r[1]); cx64(v.r[2], v.r[3]);
+        v.store(a, len);
+    }
+    __syncthreads();
+    for (u32 k = 8; k <= P; k <<= 1) {
+        const u32 kq = k >> 2;
+        // mirror k + half cleaner k/4
+        for (u32 t = threadIdx.x; t < nq; t += blockDim.x) {
+            const u32 blk = (t / kq) * k, off = t & (kq - 1);
+            Quad v;
+            v.q[0] = blk + off; v.q[1] = blk + off + kq; v.q[2] = blk + k - 1 - off - kq; v.q[3] = blk + k - 1 - off;
+            v.load(a, len);
+            cx64(v.r[0], v.r[3]); cx64(v.r[1], v.r[2]);
+            cx64(v.r[0], v.r[1]); cx64(v.r[2], v.r[3]);
+            v.store(a, len);
+        }
+        __syncthreads();
+        u32 j = k >> 3;                                  // next half cleaner
+        for (; j >= 2; j >>= 2) {                        // half cleaners j and j/2 together
+            const u32 jb = j >> 1;
+            for (u32 t = threadIdx.x; t < nq; t += blockDim.x) {
+                const u32 i = ((t & ~(jb - 1)) << 2) | (t & (jb - 1));
+                Quad v;
+                v.q[0] = i; v.q[1] = i + jb; v.q[2] = i + j; v.q[3] = i + j + jb;
+                v.load(a, len);
+                cx64(v.r[0], v.r[2]); cx64(v.r[1], v.r[3]);
+                cx64(v.r[0], v.r[1]); cx64(v.r[2], v.r[3]);
+                v.store(a, len);
+            }
+            __syncthreads();
+        }
+        if (j == 1) {                                    // one half cleaner left over
+            for (u32 t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const u32 i = 2 * t, l = i + 1;
+                if (l < len) {
+                    const u64 x = a[i], y = a[l];
+                    if (y < x) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 struct LessKey {
     static constexpr bool kUsesTag = false;
     __device__ __forceinline__ bool operator()(u64, u64 ka, u32, u64, u64 kb, u32) const { return ka < kb; }
@@ -429,7 +523,7 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
             if ((u32)(e & 15ull) != prev0) s_mixed = 1;
             const u64 sidx = (e >> 4) + depth;
             const u64 wd = text_window32(sp.codes, sidx);
-            if (!(fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes)) s_flag = 1;
+            if (!(fetch_sep(sp, sidx) == 0 && sidx + 32 <= sp.n_codes)) s_flag = 1;
             u32 lo = 0, hi = n_split;                       // first splitter >= wd
             while (lo < hi) {
                 const u32 mid = (lo + hi) >> 1;
@@ -486,7 +580,7 @@ __device__ __forceinline__ void warp_rank_short(const SpView& sp, u64* ent, u32 
     if (mem) {
         const u64 sidx = (e >> 4) + depth;
         nw = text_window32(sp.codes, sidx);
-        np = (fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
+        np = (fetch_sep(sp, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
     }
     u32 rank = 0;
     for (u32 j = 0; j < size; ++j) {
@@ -519,6 +613,7 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
     __shared__ int s_flag, s_mixed;
     __shared__ u32 s_cnt[4];
     __shared__ u32 s_list[CH / 2];         // short unresolved runs of the current item: (size << 16) | head
+    __shared__ u32 s_wm[32], s_ws[32];     // per-warp totals of the run scan (max head, prev-symbol changes)
     constexpr u32 MAX_PEEL = 64;           // dominant-word peels per item and launch
     for (u32 idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
         const WorkItem it = items[idx];
@@ -551,7 +646,7 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
                 if ((u32)(e & 15ull) != prev0) s_mixed = 1;
                 const u64 sidx = (e >> 4) + depth;
                 v.key[t] = text_window32(sp.codes, sidx);
-                const bool plain = fetch_sep(sp.sep, sidx) == 0 && sidx + 32 <= sp.n_codes;
+                const bool plain = fetch_sep(sp, sidx) == 0 && sidx + 32 <= sp.n_codes;
                 v.tag[t] = plain ? 1u : 0u;
                 if (!plain) s_flag = 1;
             }
@@ -599,10 +694,87 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
                     continue;
                 }
             }
+            if (!in_hbm) {
+                // ---- packed network (see Packed / packed_sort): order by the next ADV codes, stable ----
+                using PK = Packed<CH>;
+                constexpr int IPT = CH / NT;
+                constexpr u32 ADV = PK::ADV;
+                const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) v.key[t] = (v.key[t] & PK::WMASK) | t;
+                __syncthreads();
+                packed_sort(v.key, vlen);
+                u64 pe[IPT];
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    const u32 t = threadIdx.x + q * NT;
+                    pe[q] = t < vlen ? v.ent[v.key[t] & PK::IMASK] : 0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    const u32 t = threadIdx.x + q * NT;
+                    if (t < vlen) v.ent[t] = pe[q];
+                }
+                __syncthreads();
+                // ---- runs of equal words: one block scan gives every entry its run head (max) and the number of prev-symbol
+                //      changes inside runs before it (sum); a run is unresolved when that number grows across it ----
+                u32 hm[IPT], hs[IPT];
+                u32 rm = 0, rs = 0;
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    const u32 t = threadIdx.x * IPT + q;
+                    if (t < vlen && t > 0) {
+                        if ((v.key[t] ^ v.key[t - 1]) & PK::WMASK) rm = t;
+                        else if ((v.ent[t] ^ v.ent[t - 1]) & 15ull) ++rs;
+                    }
+                    hm[q] = rm; hs[q] = rs;
+                }
+                u32 im = rm, is = rs;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 um = __shfl_up_sync(0xffffffffu, im, o), us = __shfl_up_sync(0xffffffffu, is, o);
+                    if (lane >= (u32)o) { im = um > im ? um : im; is += us; }
+                }
+                if (lane == 31) { s_wm[warp] = im; s_ws[warp] = is; }
+                u32 pm = __shfl_up_sync(0xffffffffu, im, 1), ps = __shfl_up_sync(0xffffffffu, is, 1);
+                if (lane == 0) { pm = 0; ps = 0; }
+                __syncthreads();
+                for (u32 w2 = 0; w2 < warp; ++w2) { const u32 a = s_wm[w2]; pm = a > pm ? a : pm; ps += s_ws[w2]; }
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    const u32 t = threadIdx.x * IPT + q;
+                    hm[q] = hm[q] > pm ? hm[q] : pm;
+                    if (t < vlen) v.tag[t] = hs[q] + ps;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    const u32 t = threadIdx.x * IPT + q;
+                    if (t >= vlen) continue;
+                    if (t + 1 < vlen && !((v.key[t + 1] ^ v.key[t]) & PK::WMASK)) continue;      // not the last entry of its run
+                    const u32 h = hm[q];
+                    if (v.tag[t] == v.tag[h]) continue;                                           // one prev symbol: resolved
+                    const u32 size = t + 1 - h;
+                    if (size > 32) {
+                        WorkItem nw;
+                        nw.off = voff + h; nw.len = size; nw.depth = depth + ADV;
+                        push_item(next, nw);
+                    } else {
+                        s_list[atomicAdd(&s_cnt[3], 1u)] = (size << 16) | h;
+                    }
+                }
+                __syncthreads();
+                const u32 n_list = s_cnt[3];
+                for (u32 q = threadIdx.x >> 5; q < n_list; q += blockDim.x >> 5) {
+                    const u32 x = s_list[q];
+                    warp_rank_short(sp, v.ent + (x & 0xffffu), x >> 16, depth + ADV);
+                }
+                break;
+            }
             {
                 SegArrays gv = g;
                 gv.ent += lo; gv.key += lo; gv.tag += lo;
-                net_sort<CH>(gv, in_hbm ? s : v, vlen, !in_hbm, LessKey());
+                net_sort<CH>(gv, s, vlen, false, LessKey());
             }
             // ---- runs of equal words: head index of every entry (max-scan over "own index if head") ----
             for (u32 t = threadIdx.x; t < vlen; t += blockDim.x) v.tag[t] = (t == 0 || v.key[t] != v.key[t - 1]) ? 1u : 0u;

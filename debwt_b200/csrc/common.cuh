@@ -59,6 +59,18 @@ __host__ __device__ __forceinline__ u32 text_symbol(const u64* __restrict__ w, u
     return (u32)(w[p >> 5] >> (2 * (31 - (p & 31)))) & 3u;
 }
 
+// ---- loads the compiler must keep together and in program order (memory-level parallelism by hand) ----
+__device__ __forceinline__ u32 ld_nc_u32(const u32* p) {
+    u32 v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 ld_nc_u64x2(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+
 // ---- streaming loads / stores --------------------------------------------------------------
 __device__ __forceinline__ u64 ld_stream(const u64* p) {
     u64 v;

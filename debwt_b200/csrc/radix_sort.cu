@@ -98,7 +98,9 @@ struct SweepSmem {
 // PERSIST = false: one CTA per tile.  PERSIST = true: a resident CTA loops over tiles and issues the loads
 // of its next tile right after the current one has been reordered into shared memory, so the load latency
 // and the look-back wait of tile t overlap the global loads of tile t+1 (the key registers are free then).
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST, int LB, int SLEEP, bool PRE>
+// RANK = 1: the digit group's first lane bumps the warp histogram with one shared-memory atomic (ATOMS) and hands the old
+// count to its peers by shuffle, instead of a warp-wide load + a leader store around two warp barriers.
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST, int LB, int SLEEP, bool PRE, int RANK = 0>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 ntiles, const u64* __restrict__ gbase,
                 u64* __restrict__ lookback, u32* __restrict__ tile_counter, u64 epoch, u32* __restrict__ kidx, int kshift) {
@@ -154,11 +156,18 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 nt
         for (int j = 0; j < ITEMS; ++j) {
             const u32 d = digit_of<PASS>(key[j]);
             const u32 peers = match_digit(d);
-            const u32 pre = wh[d];
-            __syncwarp();
             const u32 below = __popc(peers & lt);
-            if (below == 0) wh[d] = pre + __popc(peers);
-            __syncwarp();
+            u32 pre;
+            if constexpr (RANK == 1) {
+                pre = 0;
+                if (below == 0) pre = atomicAdd(wh + d, (u32)__popc(peers));
+                pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
+            } else {
+                pre = wh[d];
+                __syncwarp();
+                if (below == 0) wh[d] = pre + __popc(peers);
+                __syncwarp();
+            }
             const u32 r = pre + below;
             if (j & 1) rank2[j >> 1] |= r << 16; else rank2[j >> 1] = r;
         }
@@ -265,10 +274,10 @@ onesweep_kernel(const u64* __restrict__ in, u64* __restrict__ out, u32 n, u32 nt
     }
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST, int LB, int SLEEP, bool PRE>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, int PASS, bool PERSIST, int LB, int SLEEP, bool PRE, int RANK>
 int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, cudaStream_t st) {
     using S = SweepSmem<THREADS, ITEMS>;
-    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS, PERSIST, LB, SLEEP, PRE>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, MIN_BLOCKS, PASS, PERSIST, LB, SLEEP, PRE, RANK>;
     static bool attr_done[64] = {};            // per device: function attributes belong to the device's context
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
@@ -297,17 +306,17 @@ int launch_sweep_pass(const u64* in, u64* out, u64 n, const SortWorkspace& ws, c
 }
 
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PERSIST = false, int LB = 4, int SLEEP = 0, bool PRE = false>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool PERSIST = false, int LB = 4, int SLEEP = 0, bool PRE = false, int RANK = 0>
 int launch_sweep(const u64* in, u64* out, u64 n, int pass, const SortWorkspace& ws, cudaStream_t st) {
     switch (pass) {
-        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
-        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7, PERSIST, LB, SLEEP, PRE>(in, out, n, ws, st);
+        case 0: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 0, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        case 1: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 1, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        case 2: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 2, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        case 3: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 3, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        case 4: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 4, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        case 5: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 5, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        case 6: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 6, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
+        default: return launch_sweep_pass<THREADS, ITEMS, MIN_BLOCKS, 7, PERSIST, LB, SLEEP, PRE, RANK>(in, out, n, ws, st);
     }
 }
 
@@ -330,6 +339,10 @@ int sort_config_tile(int cfg) {
         case 13: return 448 * 12;
         case 14: return 288 * 16;
         case 15: return 384 * 18;
+        case 16: return 384 * 16;
+        case 17: return 512 * 16;
+        case 18: return 256 * 16;
+        case 19: return 384 * 18;
         default: return 256 * 16;
     }
 }
@@ -407,6 +420,10 @@ int radix_sort_u64(u64* a, u64* b, u64 n, const SortWorkspace& ws, cudaStream_t 
             case 13: rc = launch_sweep<448, 12, 3>(src, dst, n, p, ws, st); break;
             case 14: rc = launch_sweep<288, 16, 4>(src, dst, n, p, ws, st); break;
             case 15: rc = launch_sweep<384, 18, 3>(src, dst, n, p, ws, st); break;
+            case 16: rc = launch_sweep<384, 16, 3, false, 4, 0, false, 1>(src, dst, n, p, ws, st); break;
+            case 17: rc = launch_sweep<512, 16, 2, false, 4, 0, false, 1>(src, dst, n, p, ws, st); break;
+            case 18: rc = launch_sweep<256, 16, 4, false, 4, 0, false, 1>(src, dst, n, p, ws, st); break;
+            case 19: rc = launch_sweep<384, 18, 3, false, 4, 0, false, 1>(src, dst, n, p, ws, st); break;
             default: rc = launch_sweep<256, 16, 3>(src, dst, n, p, ws, st); break;
         }
         if (rc) return rc;

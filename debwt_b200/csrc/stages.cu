@@ -1,6 +1,8 @@
 // Device stages around the radix sort: packing, extraction, count-by-sort, branch k-mer detection,
 // branch codes, emission.  Each kernel cites the reference loop it replaces.
 #include "stages.cuh"
+
+#include <cstdlib>
 #include "special.cuh"
 #include "stages_dev.cuh"
 #include "dist_kernels.cuh"
@@ -596,8 +598,19 @@ __global__ void __launch_bounds__(TPB) branch_index_kernel(BranchTable bt) {
 __global__ void __launch_bounds__(TPB) branch_filter_kernel(BranchTable bt) {
     const u64 b = (u64)blockIdx.x * TPB + threadIdx.x;
     if (b >= bt.n_branch) return;
-    const u64 f = bt.kmer[b] >> (64 - BranchTable::filter_bits(bt.bits));
+    const u64 f = bt.filter_of(bt.kmer[b] & ~3ull);
     atomicOr(bt.filter() + (f >> 5), 1u << (f & 31));
+}
+
+__global__ void __launch_bounds__(TPB) branch_hash_kernel(BranchTable bt) {
+    const u64 b = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (b >= bt.n_branch) return;
+    const u64 e = bt.kmer[b];
+    const u64 mask = (1ull << bt.hbits) - 1;
+    for (u64 h = bt.hash_of(e & ~3ull);; h = (h + 1) & mask) {
+        unsigned long long* claim = reinterpret_cast<unsigned long long*>(&bt.hslots[h].y);
+        if (atomicCAS(claim, 0ull, (unsigned long long)(b + 1)) == 0ull) { bt.hslots[h].x = e; return; }
+    }
 }
 
 __global__ void __launch_bounds__(TPB) special_ins_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki,
@@ -699,6 +712,15 @@ int k_branch_index(BranchTable bt, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(bt.filter(), 0, (1ull << (BranchTable::filter_bits(bt.bits) - 5)) * 4, st));
     if (bt.n_branch) branch_filter_kernel<<<grid_for(bt.n_branch, TPB), TPB, 0, st>>>(bt);
     DEBWT_COUNT(2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int k_branch_hash(BranchTable bt, cudaStream_t st) {
+    if (!bt.hslots) return 0;
+    CUDA_TRY(cudaMemsetAsync(bt.hslots, 0, (1ull << bt.hbits) * sizeof(ulonglong2), st));
+    if (bt.n_branch) branch_hash_kernel<<<grid_for(bt.n_branch, TPB), TPB, 0, st>>>(bt);
+    DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -874,67 +896,139 @@ __global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restri
 // to a dense array -- one atomic per 4096-position block, coalesced stores -- and the radix passes over the bits from
 // `shift` up group the keys by branch id, i.e. into their segments (the order inside a segment is K10's business).
 // Replaces 517 M cursor atomics and scattered 8-byte stores at 3.1 Gbp.  Needs N < 2^32 and at most 2^28 branch k-mers.
+// The lookups are staged so that many of them are in flight per thread: (A) the 16 presence-filter reads of a thread are
+// independent loads; (B) the positions that pass are compacted into a shared-memory list; (C) the index / table reads of four
+// list entries per thread are issued together; the keys are collected in shared memory and leave with one atomic per block.
+constexpr int FK_UNROLL = 4;
 __global__ void __launch_bounds__(TPB) flag_positions_keys_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                                  const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
                                                                  int shift, u32* __restrict__ mo_bits, u64* __restrict__ bkeys,
-                                                                 unsigned long long* __restrict__ counter) {
+                                                                 unsigned long long* __restrict__ counter, int dbg_stop) {
     __shared__ TileText t;
+    __shared__ u64 s_keys[TILE_POS];
+    __shared__ u16 s_hits[TILE_POS];
+    __shared__ u32 s_mo[TILE_WORDS];
     __shared__ u32 s_cnt[TILE_ROWS][TPB / 32];
+    __shared__ u32 s_nhits, s_nkeys;
     __shared__ u64 s_base;
     const u64 base = (u64)blockIdx.x * TILE_POS;
     tile_load(t, words, nwords_total, base, n, seps, n_rec);
     const bool one_record = t.rec_first == t.rec_last;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 key[TILE_ROWS];
+    if (threadIdx.x < TILE_WORDS) s_mo[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_nkeys = 0;
+    // ---- (A) presence filter of every clean position of the tile ----
+    const u32* __restrict__ filter = bt.filter();
+    u32 fw[TILE_ROWS];
+    if (one_record) {
+        // addresses first, then all loads (asm volatile keeps them together and in order: 16 requests in flight per thread),
+        // then the bit tests
+        u32 fi[TILE_ROWS];
+#pragma unroll
+        for (int j = 0; j < TILE_ROWS; ++j) {
+            const u32 local = j * TPB + threadIdx.x;
+            const u64 p = base + local;
+            const bool ok = p < n && t.rec_first < n_rec && p + KMER <= t.sep_first;
+            fi[j] = ok ? (u32)bt.filter_of(tile_window(t, local)) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < TILE_ROWS; ++j) fw[j] = ld_nc_u32(filter + (fi[j] == 0xFFFFFFFFu ? 0u : fi[j] >> 5));
+#pragma unroll
+        for (int j = 0; j < TILE_ROWS; ++j) fw[j] = fi[j] == 0xFFFFFFFFu ? 0u : (fw[j] >> (fi[j] & 31)) & 1u;
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < TILE_ROWS; ++j) {
+            const u32 local = j * TPB + threadIdx.x;
+            const u64 p = base + local;
+            bool ok = p < n;
+            if (ok) {
+                const u64 r = record_of(seps, n_rec, p);
+                ok = r < n_rec && p + KMER <= seps[r];
+            }
+            const u64 f = bt.filter_of(tile_window(t, local));
+            fw[j] = ok ? (__ldg(filter + (f >> 5)) >> (f & 31)) & 1u : 0u;
+        }
+    }
+    if (dbg_stop == 1) { u32 a = 0; for (int j = 0; j < TILE_ROWS; ++j) a += fw[j]; if (a == 77777u) mo_bits[0] = a; return; }
+    // ---- (B) compact the positions that passed ----
 #pragma unroll
     for (int j = 0; j < TILE_ROWS; ++j) {
-        const u32 local = j * TPB + threadIdx.x;
-        const u64 p = base + local;
-        bool mo = false;
-        key[j] = 0;
-        if (p < n) {
-            u64 r = t.rec_first, sep = t.sep_first, start = t.start_first;
-            bool in_text = true;
-            if (!one_record) {
-                r = record_of(seps, n_rec, p);
-                in_text = r < n_rec;
-                if (in_text) { sep = seps[r]; start = r ? seps[r - 1] + 1 : 0; }
-            }
-            if (in_text && p + KMER <= sep) {
-                const u64 x = tile_window(t, local) & ~3ull;
-                u64 b;
-                if (branch_lookup(bt, x, b)) {
-                    const u32 f = (u32)(bt.kmer[b] & 3ull);
-                    mo = f & 1u;
-                    if (f & 2u) {
-                        u32 prev;
-                        if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
-                        else prev = text_symbol(words, p - 1);
-                        key[j] = (b << shift) | (p << 4) | prev | 8ull;       // bit 3 marks "present" (b, p and prev may all be 0)
-                    }
-                }
-            }
-        }
-        const u32 bal = __ballot_sync(0xffffffffu, mo);
-        if (lane == 0 && p < n + 32) mo_bits[p >> 5] = bal;
-        const u32 bmi = __ballot_sync(0xffffffffu, key[j] != 0);
-        if (lane == 0) s_cnt[j][warp] = __popc(bmi);
+        const u32 bal = __ballot_sync(0xffffffffu, fw[j] != 0);
+        if (lane == 0) s_cnt[j][warp] = __popc(bal);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                            // 128 partial counts: serial exclusive scan, one atomic for the block
+    if (threadIdx.x == 0) {
         u32 run = 0;
         for (int j = 0; j < TILE_ROWS; ++j)
             for (int w = 0; w < TPB / 32; ++w) { const u32 c = s_cnt[j][w]; s_cnt[j][w] = run; run += c; }
-        s_base = run ? atomicAdd(counter, (unsigned long long)run) : 0;
+        s_nhits = run;
     }
     __syncthreads();
-    const u64 bb = s_base;
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < TILE_ROWS; ++j) {
-        const u32 bmi = __ballot_sync(0xffffffffu, key[j] != 0);
-        if (key[j]) bkeys[bb + s_cnt[j][warp] + __popc(bmi & lt)] = key[j];
+        const u32 bal = __ballot_sync(0xffffffffu, fw[j] != 0);
+        if (fw[j]) s_hits[s_cnt[j][warp] + __popc(bal & lt)] = (u16)(j * TPB + threadIdx.x);
     }
+    __syncthreads();
+    // ---- (C) branch-table lookups of the listed positions, FK_UNROLL per thread at a time ----
+    if (dbg_stop == 2) return;
+    const u32 nh = s_nhits;
+    const u64 hmask = (1ull << bt.hbits) - 1;
+    for (u32 c0 = 0; c0 < nh; c0 += TPB * FK_UNROLL) {
+        u32 loc[FK_UNROLL];
+        u64 x[FK_UNROLL], hs[FK_UNROLL], key[FK_UNROLL];
+        ulonglong2 v[FK_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FK_UNROLL; ++u) {
+            const u32 h = c0 + u * TPB + threadIdx.x;
+            loc[u] = h < nh ? s_hits[h] : 0xFFFFFFFFu;
+            x[u] = loc[u] != 0xFFFFFFFFu ? tile_window(t, loc[u]) & ~3ull : 0;
+            hs[u] = bt.hash_of(x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < FK_UNROLL; ++u) v[u] = ld_nc_u64x2(bt.hslots + (loc[u] != 0xFFFFFFFFu ? hs[u] : 0));
+#pragma unroll
+        for (int u = 0; u < FK_UNROLL; ++u) {
+            key[u] = 0;
+            if (loc[u] == 0xFFFFFFFFu) v[u].y = 0;
+            while (v[u].y != 0 && (v[u].x & ~3ull) != x[u]) {          // collision: next slot
+                hs[u] = (hs[u] + 1) & hmask;
+                v[u] = __ldg(bt.hslots + hs[u]);
+            }
+            if (v[u].y != 0) {
+                const u32 f = (u32)(v[u].x & 3ull);
+                if (f & 1u) atomicOr(&s_mo[loc[u] >> 5], 1u << (loc[u] & 31));
+                if (f & 2u) {
+                    const u64 p = base + loc[u];
+                    u64 r = t.rec_first, rstart = t.start_first;
+                    if (!one_record) {
+                        r = record_of(seps, n_rec, p);
+                        rstart = r ? seps[r - 1] + 1 : 0;
+                    }
+                    u32 prev;
+                    if (p == rstart) prev = r ? 4u : 5u;                    // '#' / '$'   (src/generateSP.c:584-605)
+                    else prev = text_symbol(words, p - 1);
+                    key[u] = ((v[u].y - 1) << shift) | (p << 4) | prev | 8ull;   // bit 3: "present" (id, p, prev may all be 0)
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FK_UNROLL; ++u) {                          // warp-aggregated append to the block's key list
+            const u32 bal = __ballot_sync(0xffffffffu, key[u] != 0);
+            u32 slot = 0;
+            if (lane == 0 && bal) slot = atomicAdd(&s_nkeys, (u32)__popc(bal));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (key[u]) s_keys[slot + __popc(bal & lt)] = key[u];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE_WORDS && base + 32ull * threadIdx.x < n + 32) mo_bits[(base >> 5) + threadIdx.x] = s_mo[threadIdx.x];
+    const u32 nk = s_nkeys;
+    if (threadIdx.x == 0) s_base = nk ? atomicAdd(counter, (unsigned long long)nk) : 0;
+    __syncthreads();
+    const u64 bb = s_base;
+    for (u32 i = threadIdx.x; i < nk; i += TPB) bkeys[bb + i] = s_keys[i];
 }
 
 // position -> spIndex inside the keys, in append order (positions nearly ascending: the bitmap and prefix reads are
@@ -1015,8 +1109,9 @@ int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, Bran
 
 int k_flag_positions_keys(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, int shift, u32* mo_bits,
                           u64* bkeys, u64* d_counter, cudaStream_t st) {
+    static const int dbg_stop = getenv("DEBWT_FK_STOP") ? atoi(getenv("DEBWT_FK_STOP")) : 0;
     flag_positions_keys_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, bt, shift, mo_bits, bkeys,
-                                                                      reinterpret_cast<unsigned long long*>(d_counter));
+                                                                      reinterpret_cast<unsigned long long*>(d_counter), dbg_stop);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -73,8 +73,18 @@ struct BranchTable {
     u32* blue = nullptr;   // [B+1] exclusive prefix of blue-segment sizes (0 for non multi-in)
     u32* cursor = nullptr; // [B]  fill cursor per segment
     u32* bidx = nullptr;   // [2^bits + 2] direct index on the top `bits` bits of the k-mer, followed by the
-                           // presence bitmap: one bit per value of the top filter_bits(bits) bits
+                           // presence bitmap: one bit per value of filter_of(k-mer), a filter_bits(bits)-bit HASH of the
+                           // k-mer (a prefix would let every k-mer of a repeat family through: its branch k-mers share
+                           // their first bases with the family's other k-mers)
     int bits = 0;
+    // optional hash table over the k-mers (k_branch_hash): slot = (kmer entry, branch id + 1), 0 in .y = empty, linear
+    // probing.  Branch k-mers of a repeat family share long prefixes, so the buckets of the direct index get deep there
+    // (ten dependent reads per lookup at human scale); a probe is one 16-byte read.
+    ulonglong2* hslots = nullptr;
+    int hbits = 0;
+    __host__ __device__ static int hash_bits(u64 n_branch) { int b = 10; while (b < 40 && (1ull << b) < 3 * n_branch) ++b; return b; }
+    __host__ __device__ u64 hash_of(u64 x) const { return ((x >> 2) * 0x9E3779B97F4A7C15ull) >> (64 - hbits); }
+    __host__ __device__ u64 filter_of(u64 x) const { return ((x >> 2) * 0x9E3779B97F4A7C15ull) >> (64 - filter_bits(bits)); }
     __host__ __device__ static int filter_bits(int bits) { return bits + 3 < 30 ? bits + 3 : 30; }
     __host__ __device__ static u64 index_words(int bits) { return (1ull << bits) + 2 + (1ull << (filter_bits(bits) - 5)); }
     __host__ __device__ u32* filter() const { return bidx + (1ull << bits) + 2; }
@@ -86,6 +96,8 @@ int k_branch_count(const u64* sorted, u64 n, u16* gmask, bool propagate, void* w
 // pass 2: fills kmer/head/blue (arrays must be allocated from the counts)
 int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st);
 int k_branch_index(BranchTable bt, cudaStream_t st);
+// fills bt.hslots (2^hbits slots of 16 bytes, allocated by the caller) from bt.kmer
+int k_branch_hash(BranchTable bt, cudaStream_t st);
 
 // ---- sentinel-window ("special") suffixes --------------------------------------------------
 // ins[t] = upper_bound(sorted, pad[t]) for t < m

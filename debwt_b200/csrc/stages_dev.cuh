@@ -39,8 +39,16 @@ __device__ __forceinline__ u64 group_end(const u64* __restrict__ k, u64 n, u64 i
 __device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-mer << 2, low bits 0 */, u64& b) {
     // presence bitmap first: small enough to stay in L2, it rejects most positions (branch k-mers are rare)
     // before the index and the table -- which do not fit in L2 at human scale -- are touched
-    const u64 f = x >> (64 - BranchTable::filter_bits(bt.bits));
+    const u64 f = bt.filter_of(x);
     if (!((bt.filter()[f >> 5] >> (f & 31)) & 1u)) return false;
+    if (bt.hslots) {
+        const u64 mask = (1ull << bt.hbits) - 1;
+        for (u64 h = bt.hash_of(x);; h = (h + 1) & mask) {
+            const ulonglong2 v = __ldg(bt.hslots + h);
+            if (v.y == 0) return false;
+            if ((v.x & ~3ull) == x) { b = v.y - 1; return true; }
+        }
+    }
     const u64 t = x >> (64 - bt.bits);
     u64 lo = bt.bidx[t], hi = bt.bidx[t + 1];
     while (lo < hi) {

@@ -607,8 +607,11 @@ def build_sharded(text: np.ndarray | None, seps: np.ndarray, comm: Comm, ops, st
     err = ops.zeros(4, torch.int32)
     ops.pack(ascii_slice, n_valid, my_words, wp, err)
     words = torch.cat([comm.all_gather_equal(my_words), ops.zeros(2)])
-    if int(comm.all_reduce_max(err)[0].item()):
+    err = comm.all_reduce_sum(err)
+    if int(err[0].item()):
         raise binding.DebwtError("input contains a symbol other than A, C, G, T (either case)")
+    if int(err[1].item()) != R:
+        raise binding.DebwtError("input contains '#' or '$' inside a record (they are reserved for the record separators)")
     del ascii_slice
 
     tick('pack+allgather')

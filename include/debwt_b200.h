@@ -66,8 +66,8 @@ int debwt_create(debwt_ctx** out, int device);
 void debwt_destroy(debwt_ctx* ctx);
 /* tuning knob for the sort kernel configuration (0 = default); returns the previous value */
 int debwt_set_sort_config(debwt_ctx* ctx, int cfg);
-/* how K9 brings the blue entries (src/generateSP.c:584-605) into their segments: 1 = one cursor per segment (atomics +
-   scattered stores), 2 = dense append + radix sort on the branch id, 0 (default) = 2 when there are >= 2^20 entries.
+/* how K9 brings the blue entries (src/generateSP.c:584-605) into their segments: 0 / 1 (default) = one cursor per segment
+   (atomics + scattered stores), 2 = dense append + radix sort on the branch id (measured slower at 3.1 Gbp; kept, tested).
    Same output either way; returns the previous value */
 int debwt_set_blue_grouping(debwt_ctx* ctx, int mode);
 

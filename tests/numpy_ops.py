@@ -80,6 +80,7 @@ class NumpyOps:
         sep = (a == 0x23) | (a == 0x24)
         if (~ok & ~sep).any():
             err[0] = 1
+        err[1] += int(sep.sum())
         c = ((up >> 1) & 3).astype(np.uint64)
         c ^= c >> U(1)
         code[:n_valid] = np.where(ok, c, U(3))
