@@ -474,6 +474,9 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         gbt.bits = bits;
         if (dalloc(s, &gbt.bidx, BranchTable::index_words(bits))) return -1;
         if (k_branch_index(gbt, st)) return -1;
+        gbt.hbits = BranchTable::hash_bits(B_tot);      // every rank hashes the whole table: one probe per lookup in K9
+        while (gbt.hbits > 10 && (16ull << gbt.hbits) > (4ull << 30) && (1ull << (gbt.hbits - 1)) >= B_tot + B_tot / 2) --gbt.hbits;
+        if (dalloc(s, &gbt.hslots, 1ull << gbt.hbits) || k_branch_hash(gbt, st)) return -1;
     }
     S.n_branch = B_tot; S.n_blue = M_tot;
     pc.tick("branch_table");
