@@ -455,29 +455,6 @@ __global__ void __launch_bounds__(TPB) fill_range_kernel(const u16* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(TPB) emit_blue_base_kernel(const u64* __restrict__ blue, BranchTable bt, u64 key_base,
-                                                            const u64* __restrict__ spec_ins, u64 m, u64* __restrict__ bwt,
-                                                            u64* __restrict__ sharp_rows, u32* __restrict__ sharp_count,
-                                                            u64* __restrict__ dollar_row) {
-    const u64 e = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (e >= bt.n_blue) return;
-    u64 lo = 0, hi = bt.n_branch;
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        if ((u64)bt.blue[mid] <= e) lo = mid + 1; else hi = mid;
-    }
-    const u64 b = lo - 1;
-    const u64 i = key_base + (u64)bt.head[b] + (e - bt.blue[b]);
-    const u64 row = i + upper_bound_u64(spec_ins, 0, m, i);
-    const u32 c = (u32)(blue[e] & 15ull);
-    if (c >= 4) {
-        if (c == 4) sharp_rows[atomicAdd(sharp_count, 1u)] = row; else *dollar_row = row;
-        bwt_or(bwt, row, 3u);
-    } else if (c) {
-        bwt_or(bwt, row, c);
-    }
-}
-
 }  // namespace
 
 #define LAUNCHED(k)                      \
@@ -608,14 +585,6 @@ int k_fill_range(const u16* gmask, u64 n_keys, u64 key_base, u64 n, const u64* s
     constexpr int WORDS_PER_BLOCK = (TPB / 32) * FILL_WORDS_PER_WARP;
     fill_range_kernel<<<grid_for(word_hi - word_lo, WORDS_PER_BLOCK), TPB, 0, st>>>(gmask, n_keys, key_base, n, spec_rows, m,
                                                                                     word_lo, word_hi, bwt);
-    LAUNCHED(1);
-}
-
-int k_emit_blue_base(const u64* blue, BranchTable bt, u64 key_base, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
-                     u32* d_sharp_count, u64* dollar_row, cudaStream_t st) {
-    if (bt.n_blue == 0) return 0;
-    emit_blue_base_kernel<<<grid_for(bt.n_blue, TPB), TPB, 0, st>>>(blue, bt, key_base, spec_ins, m, bwt, sharp_rows,
-                                                                    d_sharp_count, dollar_row);
     LAUNCHED(1);
 }
 

@@ -443,22 +443,15 @@ __global__ void __launch_bounds__(TPB) key_index_fill_kernel(const u64* __restri
 
 constexpr int ME_ROWS = 4;       // independent keys per thread: four search chains in flight instead of one
 
-// The in-edge join sweeps the whole key array once per first base c (queries cX ascend in X inside each
-// c block).  Thread blocks are dealt round-robin over the four c blocks, so at any time the four sweeps
-// are at about the same place in the key array and three of them hit L2 instead of HBM.
-__global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask) {
-    const u32 c = blockIdx.x & 3u;
-    const u64 chunk = blockIdx.x >> 2;
-    const u64 cbeg = ki.idx[(u64)c << (ki.bits - 2)];
-    const u64 cend = (c == 3) ? n : (u64)ki.idx[(u64)(c + 1) << (ki.bits - 2)];
-    const u64 base = cbeg + chunk * (TPB * ME_ROWS) + threadIdx.x;
-    if (cbeg + chunk * (TPB * ME_ROWS) >= cend) return;
+// In / out edge marks of ME_ROWS keys per thread: keys base + j * TPB, j < ME_ROWS, below `limit`.
+__device__ __forceinline__ void edge_rows(const u64* __restrict__ k, u64 n, const KeyIndex& ki, u16* __restrict__ gmask, u64 base,
+                                          u64 limit) {
     u64 key[ME_ROWS], lo[ME_ROWS], hi[ME_ROWS];
     bool act[ME_ROWS];
 #pragma unroll
     for (int j = 0; j < ME_ROWS; ++j) {
         const u64 i = base + (u64)j * TPB;
-        act[j] = i < cend;
+        act[j] = i < limit;
         key[j] = act[j] ? k[i] : 0;
         if (act[j] && i > 0 && k[i - 1] == key[j]) act[j] = false;     // one representative per distinct (k+1)-mer
     }
@@ -474,7 +467,7 @@ __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__
         if (!act[j]) continue;
         const u64 q = key[j] << 2;
         const u64 hs = lower_bound_u64(k, lo[j], hi[j], q);
-        if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << c);
+        if (hs < n && (k[hs] >> 2) == (q >> 2)) atomic_or_u16(gmask, hs, 1u << (u32)(key[j] >> 62));
     }
     // out edge: k-mer = first 31 bases, next symbol = last base
 #pragma unroll
@@ -482,6 +475,57 @@ __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__
         if (!act[j]) continue;
         const u64 i = base + (u64)j * TPB;
         atomic_or_u16(gmask, group_head(k, i), 1u << (GM_OUT_SHIFT + (u32)(key[j] & 3)));
+    }
+}
+
+// The in-edge join: (k+1)-mer c.X marks the group of X, and inside each first-base block c the targets ascend with the
+// sources, so the join is four merges against the whole key array.  The blocks are scheduled by TARGET: tile t of
+// ME_TILE consecutive target keys is served by four thread blocks (one per c, adjacent block ids, so they run together),
+// each of which finds by two searches the run of its c block whose targets fall into the tile.  The four runs then search
+// and mark the same 64 KB of keys / 16 KB of masks while they are in L2, and every key is fetched from HBM once as a
+// source and once as a target (the round-robin over equal SOURCE chunks this replaces drifted apart on repeat-rich
+// genomes and re-read the keys 4.7 times at 3.1 Gbp).  A run longer than ME_CAP (a highly repeated (k+1)-mer) leaves its
+// tail on a list that the whole grid works off afterwards.
+constexpr u64 ME_TILE = 8192;
+constexpr u64 ME_CAP = 8 * ME_TILE;
+struct EdgeRun { u64 begin, end; };
+
+__global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask,
+                                                        EdgeRun* __restrict__ over, u32* __restrict__ n_over) {
+    __shared__ u64 s_rng[2];
+    const u32 c = blockIdx.x & 3u;
+    const u64 tile = blockIdx.x >> 2;
+    if (threadIdx.x < 2) {
+        const u64 cbeg = ki.idx[(u64)c << (ki.bits - 2)];
+        const u64 cend = (c == 3) ? n : (u64)ki.idx[(u64)(c + 1) << (ki.bits - 2)];
+        // sources whose query (X followed by A) sorts after key a - 1 and not after key b - 1 have their lower bound in [a, b)
+        const u64 a = (tile + threadIdx.x) * ME_TILE;
+        u64 r;
+        if (a == 0) r = cbeg;
+        else if (a >= n) r = cend;
+        else {
+            const u64 low = (k[a - 1] >> 2) + 1;
+            r = (low >> 62) ? cend : indexed_lower_bound(k, ki, ((u64)c << 62) | low);
+        }
+        s_rng[threadIdx.x] = r;
+    }
+    __syncthreads();
+    const u64 sb = s_rng[0];
+    u64 se = s_rng[1];
+    if (se - sb > ME_CAP && se > sb) {
+        if (threadIdx.x == 0) over[atomicAdd(n_over, 1u)] = EdgeRun{sb + ME_CAP, se};
+        se = sb + ME_CAP;
+    }
+    for (u64 i0 = sb; i0 < se; i0 += (u64)TPB * ME_ROWS) edge_rows(k, n, ki, gmask, i0 + threadIdx.x, se);
+}
+
+__global__ void __launch_bounds__(TPB) mark_edges_over_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask,
+                                                             const EdgeRun* __restrict__ over, const u32* __restrict__ n_over) {
+    const u32 m = *n_over;
+    for (u32 q = 0; q < m; ++q) {
+        const EdgeRun r = over[q];
+        for (u64 i0 = r.begin + (u64)blockIdx.x * (TPB * ME_ROWS); i0 < r.end; i0 += (u64)gridDim.x * (TPB * ME_ROWS))
+            edge_rows(k, n, ki, gmask, i0 + threadIdx.x, r.end);
     }
 }
 
@@ -521,7 +565,7 @@ template <bool WRITE, bool PROPAGATE>
 __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, u64 n, u16* __restrict__ gmask,
                                                     u32* __restrict__ tile_nb, u32* __restrict__ tile_blue,
                                                     const u32* __restrict__ tile_nb_ex, const u32* __restrict__ tile_blue_ex,
-                                                    BranchTable bt) {
+                                                    u32* __restrict__ head_bits, BranchTable bt) {
     constexpr int NW = TPB / 32;
     __shared__ u32 s_cnt[BR_ITEMS * NW + 1], s_blue[BR_ITEMS * NW + 1];
     if (WRITE && tile_nb[blockIdx.x] == 0) return;   // the count pass found no branch group in this tile
@@ -534,21 +578,34 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
         const u64 i = base + (u64)j * TPB + threadIdx.x;
         flags[j] = 0;
         size[j] = 0;
-        if (i < n) {
-            const u64 key = k[i];
-            const bool head = (i == 0) || ((k[i - 1] >> 2) != (key >> 2));
-            if (head) {
+        if (WRITE) {
+            // the count pass left one bit per key: "heads a branch group".  Only those keys are read again (a few per cent),
+            // instead of a second sweep over all keys.
+            bal[j] = head_bits[(base + (u64)j * TPB) / 32 + warp];
+            if ((bal[j] >> lane) & 1u) {
                 const u32 m = gmask[i];
                 const u32 f = (gm_multi_out(m) ? 1u : 0u) | (gm_multi_in(m) ? 2u : 0u);
-                if (f) {
-                    flags[j] = f | 4u;
-                    if (f & 2u) size[j] = (u32)(group_end(k, n, i) - i);
-                }
-            } else if (PROPAGATE && !WRITE) {
-                gmask[i] = gmask[group_head(k, i)];
+                flags[j] = f | 4u;
+                if (f & 2u) size[j] = (u32)(group_end(k, n, i) - i);
             }
+        } else {
+            if (i < n) {
+                const u64 key = k[i];
+                const bool head = (i == 0) || ((k[i - 1] >> 2) != (key >> 2));
+                if (head) {
+                    const u32 m = gmask[i];
+                    const u32 f = (gm_multi_out(m) ? 1u : 0u) | (gm_multi_in(m) ? 2u : 0u);
+                    if (f) {
+                        flags[j] = f | 4u;
+                        if (f & 2u) size[j] = (u32)(group_end(k, n, i) - i);
+                    }
+                } else if (PROPAGATE) {
+                    gmask[i] = gmask[group_head(k, i)];
+                }
+            }
+            bal[j] = __ballot_sync(0xffffffffu, flags[j] != 0);
+            if (lane == 0) head_bits[(base + (u64)j * TPB) / 32 + warp] = bal[j];
         }
-        bal[j] = __ballot_sync(0xffffffffu, flags[j] != 0);
         u32 sz = size[j];
 #pragma unroll
         for (int o = 16; o; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
@@ -645,10 +702,19 @@ int k_build_key_index(const u64* sorted, u64 n, KeyIndex ki, cudaStream_t st) {
 
 int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t st) {
     if (n == 0) return 0;
-    // four interleaved streams; each gets enough blocks for the largest possible c block
-    mark_edges_kernel<<<4 * (grid_for(n, TPB * ME_ROWS) + 1), TPB, 0, st>>>(sorted, n, ki, gmask);
-    DEBWT_COUNT(1);
-    CUDA_TRY(cudaGetLastError());
+    const u64 tiles = (n + ME_TILE - 1) / ME_TILE;
+    const u64 cap = n / ME_CAP + 8;                          // runs that can exceed ME_CAP
+    char* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), 16 + cap * sizeof(EdgeRun), st));
+    u32* n_over = reinterpret_cast<u32*>(ws);
+    EdgeRun* over = reinterpret_cast<EdgeRun*>(ws + 16);
+    cudaMemsetAsync(n_over, 0, 16, st);
+    mark_edges_kernel<<<(unsigned)(4 * tiles), TPB, 0, st>>>(sorted, n, ki, gmask, over, n_over);
+    mark_edges_over_kernel<<<148 * 8, TPB, 0, st>>>(sorted, n, ki, gmask, over, n_over);
+    DEBWT_COUNT(2);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) { set_error(std::string("mark_edges: ") + cudaGetErrorString(e)); return -1; }
     return 0;
 }
 
@@ -669,7 +735,7 @@ int k_propagate(const u64* sorted, u64 n, u16* gmask, cudaStream_t st) {
 }
 
 namespace {
-struct BranchWs { u32 *nb, *blue, *nb_ex, *blue_ex; void* scan_ws; u64 nt; };
+struct BranchWs { u32 *nb, *blue, *nb_ex, *blue_ex, *head_bits; void* scan_ws; u64 nt; };
 BranchWs branch_ws(void* workspace, u64 n) {
     BranchWs w;
     w.nt = (n + BR_TILE - 1) / BR_TILE;
@@ -678,20 +744,22 @@ BranchWs branch_ws(void* workspace, u64 n) {
     char* q = reinterpret_cast<char*>(p + 4 * w.nt);
     q += (8 - (reinterpret_cast<uintptr_t>(q) & 7)) & 7;
     w.scan_ws = q;
+    q += (scan_workspace_bytes(w.nt + 1) + 15) & ~(size_t)15;
+    w.head_bits = reinterpret_cast<u32*>(q);          // one bit per key, BR_TILE / 32 words per tile
     return w;
 }
 }  // namespace
 
 size_t branch_workspace_bytes(u64 n) {
     const u64 nt = (n + BR_TILE - 1) / BR_TILE + 1;
-    return nt * 16 + 16 + scan_workspace_bytes(nt);
+    return nt * 16 + 16 + scan_workspace_bytes(nt) + 32 + nt * (BR_TILE / 8);
 }
 
 int k_branch_count(const u64* sorted, u64 n, u16* gmask, bool propagate, void* workspace, u64* d_totals, cudaStream_t st) {
     BranchWs w = branch_ws(workspace, n);
     BranchTable none;
-    if (propagate) branch_kernel<false, true><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, none);
-    else branch_kernel<false, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, none);
+    if (propagate) branch_kernel<false, true><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, w.head_bits, none);
+    else branch_kernel<false, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, gmask, w.nb, w.blue, nullptr, nullptr, w.head_bits, none);
     DEBWT_COUNT(1);
     if (scan_exclusive_u32(w.nb, w.nb_ex, w.nt, false, w.scan_ws, d_totals, st)) return -1;
     if (scan_exclusive_u32(w.blue, w.blue_ex, w.nt, false, w.scan_ws, d_totals + 1, st)) return -1;
@@ -701,7 +769,7 @@ int k_branch_count(const u64* sorted, u64 n, u16* gmask, bool propagate, void* w
 
 int k_branch_write(const u64* sorted, u64 n, const u16* gmask, void* workspace, BranchTable bt, cudaStream_t st) {
     BranchWs w = branch_ws(workspace, n);
-    branch_kernel<true, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, const_cast<u16*>(gmask), w.nb, nullptr, w.nb_ex, w.blue_ex, bt);
+    branch_kernel<true, false><<<(unsigned)w.nt, TPB, 0, st>>>(sorted, n, const_cast<u16*>(gmask), w.nb, nullptr, w.nb_ex, w.blue_ex, w.head_bits, bt);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1205,27 +1273,50 @@ __global__ void __launch_bounds__(TPB) fill_case2_kernel(const u16* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(TPB) emit_blue_kernel(const u64* __restrict__ blue, BranchTable bt,
+// A block owns EB_ITEMS * TPB consecutive blue entries.  Their segments are consecutive branch entries and their rows
+// ascend, so the block looks up the branch range and the sentinel range of its first and last entry once, and every
+// entry only searches inside those (a handful of steps instead of log2(B) + log2(32 R) per entry).
+constexpr int EB_ITEMS = 8;
+__global__ void __launch_bounds__(TPB) emit_blue_kernel(const u64* __restrict__ blue, BranchTable bt, u64 key_base,
                                                        const u64* __restrict__ spec_ins, u64 m, u64* __restrict__ bwt,
                                                        u64* __restrict__ sharp_rows, u32* __restrict__ sharp_count,
                                                        u64* __restrict__ dollar_row) {
-    const u64 e = (u64)blockIdx.x * TPB + threadIdx.x;
-    if (e >= bt.n_blue) return;
-    // segment = last branch entry whose blue offset is <= e
-    u64 lo = 0, hi = bt.n_branch;
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        if ((u64)bt.blue[mid] <= e) lo = mid + 1; else hi = mid;
+    __shared__ u64 s_b[2], s_t[2];
+    const u64 e0 = (u64)blockIdx.x * (EB_ITEMS * TPB);
+    const u64 e1 = e0 + EB_ITEMS * TPB < bt.n_blue ? e0 + EB_ITEMS * TPB : bt.n_blue;      // exclusive
+    if (threadIdx.x < 2) {
+        // segment = last branch entry whose blue offset is <= e
+        const u64 e = threadIdx.x == 0 ? e0 : e1 - 1;
+        u64 lo = 0, hi = bt.n_branch;
+        while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((u64)bt.blue[mid] <= e) lo = mid + 1; else hi = mid;
+        }
+        const u64 b = lo - 1;
+        s_b[threadIdx.x] = b;
+        s_t[threadIdx.x] = upper_bound_u64(spec_ins, 0, m, key_base + (u64)bt.head[b] + (e - bt.blue[b]));
     }
-    const u64 b = lo - 1;
-    const u64 i = (u64)bt.head[b] + (e - bt.blue[b]);
-    const u64 row = i + upper_bound_u64(spec_ins, 0, m, i);
-    const u32 c = (u32)(blue[e] & 15ull);
-    if (c >= 4) {
-        if (c == 4) sharp_rows[atomicAdd(sharp_count, 1u)] = row; else *dollar_row = row;
-        bwt_or(bwt, row, 3u);                                   // '#'/'$' stored as T (src/insertCase3.c:84-95)
-    } else if (c) {
-        bwt_or(bwt, row, c);
+    __syncthreads();
+    const u64 b_lo = s_b[0], b_hi = s_b[1], t_lo = s_t[0], t_hi = s_t[1];
+#pragma unroll
+    for (int j = 0; j < EB_ITEMS; ++j) {
+        const u64 e = e0 + (u64)j * TPB + threadIdx.x;
+        if (e >= e1) break;
+        u64 lo = b_lo, hi = b_hi + 1;                        // the answer lies in [b_lo, b_hi]
+        while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((u64)bt.blue[mid] <= e) lo = mid + 1; else hi = mid;
+        }
+        const u64 b = lo - 1;
+        const u64 i = key_base + (u64)bt.head[b] + (e - bt.blue[b]);
+        const u64 row = i + upper_bound_u64(spec_ins, t_lo, t_hi, i);
+        const u32 c = (u32)(blue[e] & 15ull);
+        if (c >= 4) {
+            if (c == 4) sharp_rows[atomicAdd(sharp_count, 1u)] = row; else *dollar_row = row;
+            bwt_or(bwt, row, 3u);                                   // '#'/'$' stored as T (src/insertCase3.c:84-95)
+        } else if (c) {
+            bwt_or(bwt, row, c);
+        }
     }
 }
 
@@ -1246,14 +1337,19 @@ int k_fill_case2(const u16* gmask, u64 n_keys, u64 n, const u64* spec_rows, u64 
     return 0;
 }
 
-int k_emit_blue(const u64* blue, BranchTable bt, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
-                u32* d_sharp_count, u64* dollar_row, cudaStream_t st) {
+int k_emit_blue_base(const u64* blue, BranchTable bt, u64 key_base, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
+                     u32* d_sharp_count, u64* dollar_row, cudaStream_t st) {
     if (bt.n_blue == 0) return 0;
-    emit_blue_kernel<<<grid_for(bt.n_blue, TPB), TPB, 0, st>>>(blue, bt, spec_ins, m, bwt, sharp_rows, d_sharp_count,
-                                                               dollar_row);
+    emit_blue_kernel<<<grid_for(bt.n_blue, EB_ITEMS * TPB), TPB, 0, st>>>(blue, bt, key_base, spec_ins, m, bwt, sharp_rows,
+                                                                          d_sharp_count, dollar_row);
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int k_emit_blue(const u64* blue, BranchTable bt, const u64* spec_ins, u64 m, u64* bwt, u64* sharp_rows,
+                u32* d_sharp_count, u64* dollar_row, cudaStream_t st) {
+    return k_emit_blue_base(blue, bt, 0, spec_ins, m, bwt, sharp_rows, d_sharp_count, dollar_row, st);
 }
 
 int k_emit_special(const u64* spec_rows, const u8* spec_chr, u64 m, u64* bwt, cudaStream_t st) {
