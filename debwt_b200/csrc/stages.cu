@@ -607,8 +607,10 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
             if (lane == 0) head_bits[(base + (u64)j * TPB) / 32 + warp] = bal[j];
         }
         u32 sz = size[j];
+        if (bal[j]) {                                 // warp-uniform: most rows hold no branch head
 #pragma unroll
-        for (int o = 16; o; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            for (int o = 16; o; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        }
         if (lane == 0) { s_cnt[j * NW + warp] = __popc(bal[j]); s_blue[j * NW + warp] = sz; }
     }
     __syncthreads();
@@ -628,6 +630,7 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
     const u32 ol0 = tile_blue_ex[blockIdx.x];
 #pragma unroll
     for (int j = 0; j < BR_ITEMS; ++j) {
+        if (bal[j] == 0) continue;                    // warp-uniform
         // exclusive prefix of the sizes inside the warp row
         u32 inc = size[j];
 #pragma unroll
