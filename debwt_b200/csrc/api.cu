@@ -405,7 +405,14 @@ int debwt_build(debwt_ctx* c, int k) {
         CUDA_TRY(cudaMemcpyAsync(bt.blue + bt.n_branch, &m32, 4, cudaMemcpyHostToDevice, st));
     }
     if (k_branch_index(bt, st)) return -1;
+    // blue entries into their segments: by a cursor per segment (kept in the hash slot of the k-mer), or appended densely
+    // and grouped by a radix sort on the branch id (the id sits at the top of the key, so ceil(bits / 8) passes do it)
+    int id_bits = 1;
+    while (id_bits < 64 && (bt.n_branch >> id_bits)) ++id_bits;
+    const bool group_by_sort = id_bits <= 28 && n < (1ull << 32) && bt.n_blue > 1 &&
+                               c->blue_grouping == 2;      // measured at 3.1 Gbp: 84 ms against 70 ms for the cursors
     bt.hbits = BranchTable::hash_bits(bt.n_branch);
+    bt.hmode = group_by_sort ? 0 : 1;
     if (dalloc(pool, &bt.hslots, 1ull << bt.hbits) || k_branch_hash(bt, st)) return -1;
     mark();                                                                     // ev4
 
@@ -443,12 +450,6 @@ int debwt_build(debwt_ctx* c, int k) {
     u32 *d_mo = nullptr, *d_wp = nullptr;
     u64* d_blue = nullptr;
     void* d_scanws = nullptr;
-    // blue entries into their segments: by a cursor per segment, or appended densely and grouped by a radix sort on the
-    // branch id (the id sits at the top of the key, so ceil(bits / 8) passes do it)
-    int id_bits = 1;
-    while (id_bits < 64 && (bt.n_branch >> id_bits)) ++id_bits;
-    const bool group_by_sort = id_bits <= 28 && n < (1ull << 32) && bt.n_blue > 1 &&
-                               c->blue_grouping == 2;      // measured at 3.1 Gbp: 84 ms against 70 ms for the cursors
     const int id_shift = 64 - id_bits;
     u64 *d_bka = nullptr, *d_bkb = nullptr, *d_bcount = nullptr;
     void* d_bsortws = nullptr;
@@ -489,6 +490,9 @@ int debwt_build(debwt_ctx* c, int k) {
         if (k_blue_keys_strip(d_blue, bt.n_blue, st)) return -1;
         pool.adopt(d_blue == d_bka ? d_bkb : d_bka, (bt.n_blue + 2) * 8);
         pool.adopt(d_bsortws, sort_workspace_bytes(bt.n_blue, bcfg));
+    } else if (bt.n_blue >= nbw / 4) {
+        u64* d_mw = nullptr;
+        if (dalloc(pool, &d_mw, nbw + 2) || k_blue_fix_interleaved(d_blue, bt.n_blue, d_mo, d_wp, nbw + 1, d_mw, st)) return -1;
     } else if (k_blue_fix(d_blue, bt.n_blue, d_mo, d_wp, st)) return -1;
     u64 dollar_index = 0;
     CUDA_TRY(cudaMemcpyAsync(&dollar_index, d_tail_idx + (R - 1), 8, cudaMemcpyDeviceToHost, st));

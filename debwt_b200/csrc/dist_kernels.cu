@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(TPB) flag_slice_kernel(const u64* __restrict__
         if (r < n_rec && p + KMER <= seps[r]) {
             const u64 x = text_window32(words, p) & ~3ull;
             u64 b;
-            if (branch_lookup(bt, x, b)) {
-                const u32 f = (u32)(bt.kmer[b] & 3ull);
+            u32 f;
+            if (branch_lookup(bt, x, b, f)) {
                 mo = f & 1u;
                 if (f & 2u) {
                     const u64 start = r ? seps[r - 1] + 1 : 0;

@@ -77,11 +77,14 @@ struct BranchTable {
                            // k-mer (a prefix would let every k-mer of a repeat family through: its branch k-mers share
                            // their first bases with the family's other k-mers)
     int bits = 0;
-    // optional hash table over the k-mers (k_branch_hash): slot = (kmer entry, branch id + 1), 0 in .y = empty, linear
-    // probing.  Branch k-mers of a repeat family share long prefixes, so the buckets of the direct index get deep there
-    // (ten dependent reads per lookup at human scale); a probe is one 16-byte read.
+    // optional hash table over the k-mers (k_branch_hash): slot.x = kmer entry (never 0: a branch entry has a flag set;
+    // 0 = empty slot), linear probing.  Branch k-mers of a repeat family share long prefixes, so the buckets of the direct
+    // index get deep there (ten dependent reads per lookup at human scale); a probe is one 16-byte read.
+    // slot.y: hmode 0 = branch id; hmode 1 = (blue offset << 32) | fill cursor of the k-mer's segment, so that K9 claims the
+    // place of a blue entry with one 64-bit atomic on the sector it has just read (no reads of blue[] / cursor[]).
     ulonglong2* hslots = nullptr;
     int hbits = 0;
+    int hmode = 0;
     __host__ __device__ static int hash_bits(u64 n_branch) { int b = 10; while (b < 40 && (1ull << b) < 3 * n_branch) ++b; return b; }
     __host__ __device__ u64 hash_of(u64 x) const { return ((x >> 2) * 0x9E3779B97F4A7C15ull) >> (64 - hbits); }
     __host__ __device__ u64 filter_of(u64 x) const { return ((x >> 2) * 0x9E3779B97F4A7C15ull) >> (64 - filter_bits(bits)); }
@@ -115,6 +118,9 @@ int k_flag_positions_keys(const u64* words, u64 n, const u64* d_seps, u64 n_rec,
                           u64* bkeys, u64* d_counter, cudaStream_t st);
 int k_blue_keys_fix(u64* bkeys, u64 m, const u32* mo_bits, const u32* word_prefix, cudaStream_t st);
 int k_blue_keys_strip(u64* bkeys, u64 m, cudaStream_t st);
+// blue entries: position -> spIndex (k_blue_fix), or the same through an interleaved copy of the bitmap and its prefix
+// (scratch: n_words u64, n_words = words of mo_bits) when there are enough entries to pay for the copy
+int k_blue_fix_interleaved(u64* blue, u64 m, const u32* mo_bits, const u32* word_prefix, u64 n_words, u64* scratch, cudaStream_t st);
 int k_patch_bits(u32* mo_bits, const u64* positions, u64 m, cudaStream_t st);
 // sp_codes: ceil(S/32)+3 u64 zeroed; codes packed 32 per word, code j at bits 2*(31-(j&31))
 int k_emit_codes(const u64* words, u64 n, const u32* mo_bits, const u32* word_prefix, u64* sp_codes, cudaStream_t st);

@@ -36,17 +36,18 @@ __device__ __forceinline__ u64 group_end(const u64* __restrict__ k, u64 n, u64 i
 }
 
 
-__device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-mer << 2, low bits 0 */, u64& b) {
+// b: branch id (hash table in hmode 1: the slot index instead); f: the entry's flags (multi_in << 1 | multi_out)
+__device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-mer << 2, low bits 0 */, u64& b, u32& f) {
     // presence bitmap first: small enough to stay in L2, it rejects most positions (branch k-mers are rare)
-    // before the index and the table -- which do not fit in L2 at human scale -- are touched
-    const u64 f = bt.filter_of(x);
-    if (!((bt.filter()[f >> 5] >> (f & 31)) & 1u)) return false;
+    // before the table -- which does not fit in L2 at human scale -- is touched
+    const u64 fi = bt.filter_of(x);
+    if (!((bt.filter()[fi >> 5] >> (fi & 31)) & 1u)) return false;
     if (bt.hslots) {
         const u64 mask = (1ull << bt.hbits) - 1;
         for (u64 h = bt.hash_of(x);; h = (h + 1) & mask) {
             const ulonglong2 v = __ldg(bt.hslots + h);
-            if (v.y == 0) return false;
-            if ((v.x & ~3ull) == x) { b = v.y - 1; return true; }
+            if (v.x == 0) return false;
+            if ((v.x & ~3ull) == x) { b = bt.hmode ? h : v.y; f = (u32)(v.x & 3ull); return true; }
         }
     }
     const u64 t = x >> (64 - bt.bits);
@@ -56,7 +57,10 @@ __device__ __forceinline__ bool branch_lookup(const BranchTable& bt, u64 x /* k-
         u64 v = bt.kmer[mid] & ~3ull;
         if (v < x) lo = mid + 1; else hi = mid;
     }
-    if (lo < bt.n_branch && (bt.kmer[lo] & ~3ull) == x) { b = lo; return true; }
+    if (lo < bt.n_branch) {
+        const u64 v = bt.kmer[lo];
+        if ((v & ~3ull) == x) { b = lo; f = (u32)(v & 3ull); return true; }
+    }
     return false;
 }
 
