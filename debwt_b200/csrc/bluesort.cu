@@ -44,6 +44,16 @@ __device__ __forceinline__ u32 fetch_sep(const SpView& v, u64 s) {
     return (lo >> sh) | (sep[i + 1] << (32 - sh));
 }
 
+// separator flags of the 32 codes from s on, for the sites that fetch one window per entry: summary first
+__device__ __forceinline__ u32 sep_window(const SpView& v, u64 s) {
+    if (v.sep_sum) {
+        const u64 i = s >> 5, j0 = i >> 5, j1 = (i + 1) >> 5;
+        const u32 b0 = (__ldg(v.sep_sum + (j0 >> 5)) >> (j0 & 31)) & 1u, b1 = (__ldg(v.sep_sum + (j1 >> 5)) >> (j1 & 31)) & 1u;
+        if (!(b0 | b1)) return 0u;
+    }
+    return fetch_sep(v, s);
+}
+
 // strict "string at sa < string at sb" starting the comparison `skip` codes in; sa != sb
 __device__ __forceinline__ bool sp_less_from(const SpView& v, u64 sa, u64 sb, u32 skip) {
     sa += skip;
@@ -76,7 +86,7 @@ __device__ __forceinline__ Cached cache_of(const SpView& v, u64 entry) {
     const u64 s = entry >> 4;
     Cached c;
     c.word = text_window32(v.codes, s);
-    c.plain = fetch_sep(v, s) == 0;
+    c.plain = sep_window(v, s) == 0;
     return c;
 }
 
@@ -87,6 +97,12 @@ __device__ __forceinline__ bool entry_less(const SpView& v, u64 ea, u64 wa, bool
         return sp_less_from(v, ea >> 4, eb >> 4, 32);
     }
     return sp_less_from(v, ea >> 4, eb >> 4, 0);
+}
+
+// summary of the separator bitmap: bit j = some word of sep[32 j, 32 j + 32) is non-zero
+__global__ void __launch_bounds__(TPB) sep_summary_kernel(const u32* __restrict__ sep, u64 nwords, u32* __restrict__ sum) {
+    const u64 i = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (i < nwords && sep[i]) atomicOr(sum + (i >> 10), 1u << ((i >> 5) & 31));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
             if ((u32)(e & 15ull) != prev0) s_mixed = 1;
             const u64 sidx = (e >> 4) + depth;
             const u64 wd = text_window32(sp.codes, sidx);
-            if (!(fetch_sep(sp, sidx) == 0 && sidx + 32 <= sp.n_codes)) s_flag = 1;
+            if (!(sep_window(sp, sidx) == 0 && sidx + 32 <= sp.n_codes)) s_flag = 1;
             u32 lo = 0, hi = n_split;                       // first splitter >= wd
             while (lo < hi) {
                 const u32 mid = (lo + hi) >> 1;
@@ -593,7 +609,7 @@ __device__ __forceinline__ void warp_rank_short(const SpView& sp, u64* ent, u32 
     if (mem) {
         const u64 sidx = (e >> 4) + depth;
         nw = text_window32(sp.codes, sidx);
-        np = (fetch_sep(sp, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
+        np = (sep_window(sp, sidx) == 0 && sidx + 32 <= sp.n_codes) ? 1u : 0u;
     }
     u32 rank = 0;
     for (u32 j = 0; j < size; ++j) {
@@ -659,7 +675,7 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
                 if ((u32)(e & 15ull) != prev0) s_mixed = 1;
                 const u64 sidx = (e >> 4) + depth;
                 v.key[t] = text_window32(sp.codes, sidx);
-                const bool plain = fetch_sep(sp, sidx) == 0 && sidx + 32 <= sp.n_codes;
+                const bool plain = sep_window(sp, sidx) == 0 && sidx + 32 <= sp.n_codes;
                 v.tag[t] = plain ? 1u : 0u;
                 if (!plain) s_flag = 1;
             }
@@ -851,6 +867,19 @@ __global__ void __launch_bounds__(NT, MINB) refine_kernel(u64* __restrict__ blue
 // d_work: 8 counter words + 4 lists of n_branch entries each (u32) => 4 * n_branch + 16 words
 int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t st) {
     if (bt.n_blue == 0 || bt.n_branch == 0) return 0;
+    u32* d_sum = nullptr;
+    struct SumFree {                        // lives outside the build arena: hand it back on every exit path
+        cudaStream_t st;
+        u32** p;
+        ~SumFree() { if (*p) cudaFreeAsync(*p, st); }
+    } sum_guard{st, &d_sum};
+    {
+        const u64 nsw = sp.n_codes / 32 + 2, sum_words = (nsw >> 10) + 4;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_sum), sum_words * 4, st));
+        CUDA_TRY(cudaMemsetAsync(d_sum, 0, sum_words * 4, st));
+        sep_summary_kernel<<<(unsigned)((nsw + TPB - 1) / TPB), TPB, 0, st>>>(sp.sep, nsw, d_sum);
+        sp.sep_sum = d_sum;
+    }
     u32* counts = d_work;
     u32* small = d_work + 8;
     u32* mid = small + bt.n_branch;
@@ -861,7 +890,7 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
     u32 h[4];
     CUDA_TRY(cudaMemcpyAsync(h, counts, sizeof h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    int launched = 1;
+    int launched = 2;
     auto blocks_for = [](u32 warps) { u32 b = (warps + WARPS - 1) / WARPS; return b > 148u * 16u ? 148u * 16u : (b ? b : 1u); };
     if (h[0]) { sort_small_kernel<<<blocks_for(h[0]), TPB, 0, st>>>(blue, bt, sp, small, counts + 0); ++launched; }
     if (h[1]) { sort_mid_kernel<<<blocks_for(h[1]), TPB, 0, st>>>(blue, bt, sp, mid, counts + 1); ++launched; }

@@ -135,6 +135,10 @@ struct SpView {
     const u32* sep;     // 1 bit per code: code is '#' or '$'
     u64 dollar_index;   // index of the one '$' code
     u64 n_codes;        // S
+    const u32* sep_sum = nullptr;   // optional (k_sort_blue builds it): bit j = some word of sep[32 j, 32 j + 32) is non-zero.  Only
+                                    // R separator codes exist, so the one-fetch-per-entry sites test this 64 KB summary and
+                                    // leave the S/8-byte bitmap alone (not the string walks: there the extra dependent load costs
+                                    // more than the sector it saves)
 };
 int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work /* >= 4 B + 16 u32 */, cudaStream_t st);
 
