@@ -589,19 +589,31 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
                 if (f & 2u) size[j] = (u32)(group_end(k, n, i) - i);
             }
         } else {
-            if (i < n) {
+            const bool valid = i < n;
+            bool head = false;
+            u32 m = 0;
+            if (valid) {
                 const u64 key = k[i];
-                const bool head = (i == 0) || ((k[i - 1] >> 2) != (key >> 2));
+                head = (i == 0) || ((k[i - 1] >> 2) != (key >> 2));
                 if (head) {
-                    const u32 m = gmask[i];
+                    m = gmask[i];
                     const u32 f = (gm_multi_out(m) ? 1u : 0u) | (gm_multi_in(m) ? 2u : 0u);
                     if (f) {
                         flags[j] = f | 4u;
                         if (f & 2u) size[j] = (u32)(group_end(k, n, i) - i);
                     }
-                } else if (PROPAGATE) {
-                    gmask[i] = gmask[group_head(k, i)];
                 }
+            }
+            if (PROPAGATE) {
+                // every member of a group gets its head's mask: from the nearest head to the left in the warp row (shuffle);
+                // the lanes before the row's first head all belong to lane 0's group: one search for the warp
+                const u32 hb = __ballot_sync(0xffffffffu, head);
+                const u32 mine = hb & (lt | (1u << lane));
+                const u32 got = __shfl_sync(0xffffffffu, m, mine ? 31 - __clz(mine) : 0);
+                u32 lead = 0;
+                if (lane == 0 && valid && !head) lead = gmask[group_head(k, i)];
+                lead = __shfl_sync(0xffffffffu, lead, 0);
+                if (valid && !head) gmask[i] = (u16)(mine ? got : lead);
             }
             bal[j] = __ballot_sync(0xffffffffu, flags[j] != 0);
             if (lane == 0) head_bits[(base + (u64)j * TPB) / 32 + warp] = bal[j];
@@ -924,6 +936,11 @@ int k_special_insertion(const u64* sorted, u64 n, KeyIndex ki, const u64* pads, 
 // =============================================================================================
 namespace {
 
+// Memory-level parallelism by hand: a thread first issues the presence-filter reads of its 16 positions together, then the
+// hash-table probes of the positions that passed, four at a time (the straightforward loop kept one dependent read in
+// flight per thread and spent 60 % of its time waiting for the filter and the probe).  No block-wide compaction: the
+// candidates of a thread are a 16-bit mask.
+constexpr int FP_BATCH = 4;
 __global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                             const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
                                                             u32* __restrict__ mo_bits, u64* __restrict__ blue) {
@@ -931,42 +948,106 @@ __global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restri
     const u64 base = (u64)blockIdx.x * TILE_POS;
     tile_load(t, words, nwords_total, base, n, seps, n_rec);
     const bool one_record = t.rec_first == t.rec_last;
-#pragma unroll 4
-    for (int j = 0; j < TILE_ROWS; ++j) {
-        const u32 local = j * TPB + threadIdx.x;
-        const u64 p = base + local;
-        bool mo = false;
-        if (p < n) {
+    const u32* __restrict__ filter = bt.filter();
+    u32 cand = 0, mo_mask = 0;                               // bit j: position j * TPB + tid
+    if (one_record && bt.hslots) {
+        u32 fi[TILE_ROWS], fw[TILE_ROWS];
+#pragma unroll
+        for (int j = 0; j < TILE_ROWS; ++j) {
+            const u32 local = j * TPB + threadIdx.x;
+            const u64 p = base + local;
+            const bool ok = p < n && t.rec_first < n_rec && p + KMER <= t.sep_first;
+            fi[j] = ok ? (u32)bt.filter_of(tile_window(t, local)) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < TILE_ROWS; ++j) fw[j] = ld_nc_u32(filter + (fi[j] == 0xFFFFFFFFu ? 0u : fi[j] >> 5));
+#pragma unroll
+        for (int j = 0; j < TILE_ROWS; ++j)
+            if (fi[j] != 0xFFFFFFFFu && ((fw[j] >> (fi[j] & 31)) & 1u)) cand |= 1u << j;
+        const u64 hmask = (1ull << bt.hbits) - 1;
+        while (cand) {
+            u32 loc[FP_BATCH];
+            u64 x[FP_BATCH], hs[FP_BATCH];
+            ulonglong2 v[FP_BATCH];
+#pragma unroll
+            for (int u = 0; u < FP_BATCH; ++u) {
+                loc[u] = 0xFFFFFFFFu;
+                x[u] = 0; hs[u] = 0;
+                if (cand) {
+                    const int j = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    loc[u] = j * TPB + threadIdx.x;
+                    x[u] = tile_window(t, loc[u]) & ~3ull;
+                    hs[u] = bt.hash_of(x[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FP_BATCH; ++u) v[u] = ld_nc_u64x2(bt.hslots + hs[u]);
+#pragma unroll
+            for (int u = 0; u < FP_BATCH; ++u) {
+                if (loc[u] == 0xFFFFFFFFu) continue;
+                while (v[u].x != 0 && (v[u].x & ~3ull) != x[u]) {      // collision: next slot
+                    hs[u] = (hs[u] + 1) & hmask;
+                    v[u] = __ldg(bt.hslots + hs[u]);
+                }
+                if (v[u].x == 0) continue;
+                const u32 f = (u32)(v[u].x & 3ull);
+                if (f & 1u) mo_mask |= 1u << (loc[u] / TPB);
+                if (f & 2u) {
+                    const u64 p = base + loc[u];
+                    u32 prev;
+                    if (p == t.start_first) prev = t.rec_first ? 4u : 5u;      // '#' / '$'   (src/generateSP.c:584-605)
+                    else prev = text_symbol(words, p - 1);
+                    u64 at;
+                    if (bt.hmode) {                                            // offset and cursor live in the slot just read
+                        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(&bt.hslots[hs[u]].y), 1ull);
+                        at = (old >> 32) + (old & 0xFFFFFFFFull);
+                    } else {
+                        const u64 b = v[u].y;
+                        at = (u64)bt.blue[b] + atomicAdd(bt.cursor + b, 1u);
+                    }
+                    blue[at] = (p << 4) | prev;
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < TILE_ROWS; ++j) {
+            const u32 local = j * TPB + threadIdx.x;
+            const u64 p = base + local;
+            if (p >= n) continue;
             u64 r = t.rec_first, sep = t.sep_first, start = t.start_first;
-            bool in_text = true;
+            bool in_text = r < n_rec;
             if (!one_record) {
                 r = record_of(seps, n_rec, p);
                 in_text = r < n_rec;
                 if (in_text) { sep = seps[r]; start = r ? seps[r - 1] + 1 : 0; }
             }
-            if (in_text && p + KMER <= sep) {
-                const u64 x = tile_window(t, local) & ~3ull;
-                u64 b;
-                u32 f;
-                if (branch_lookup(bt, x, b, f)) {
-                    mo = f & 1u;
-                    if (f & 2u) {
-                        u32 prev;
-                        if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
-                        else prev = text_symbol(words, p - 1);
-                        u64 at;
-                        if (bt.hslots && bt.hmode) {                        // offset and cursor live in the slot just read
-                            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(&bt.hslots[b].y), 1ull);
-                            at = (old >> 32) + (old & 0xFFFFFFFFull);
-                        } else {
-                            at = (u64)bt.blue[b] + atomicAdd(bt.cursor + b, 1u);
-                        }
-                        blue[at] = (p << 4) | prev;
-                    }
+            if (!(in_text && p + KMER <= sep)) continue;
+            const u64 x = tile_window(t, local) & ~3ull;
+            u64 b;
+            u32 f;
+            if (!branch_lookup(bt, x, b, f)) continue;
+            if (f & 1u) mo_mask |= 1u << j;
+            if (f & 2u) {
+                u32 prev;
+                if (p == start) prev = r ? 4u : 5u;                 // '#' / '$'   (src/generateSP.c:584-605)
+                else prev = text_symbol(words, p - 1);
+                u64 at;
+                if (bt.hslots && bt.hmode) {
+                    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(&bt.hslots[b].y), 1ull);
+                    at = (old >> 32) + (old & 0xFFFFFFFFull);
+                } else {
+                    at = (u64)bt.blue[b] + atomicAdd(bt.cursor + b, 1u);
                 }
+                blue[at] = (p << 4) | prev;
             }
         }
-        const u32 bal = __ballot_sync(0xffffffffu, mo);
+    }
+#pragma unroll
+    for (int j = 0; j < TILE_ROWS; ++j) {
+        const u64 p = base + (u64)j * TPB + threadIdx.x;
+        const u32 bal = __ballot_sync(0xffffffffu, (mo_mask >> j) & 1u);
         if ((threadIdx.x & 31) == 0 && p < n + 32) mo_bits[p >> 5] = bal;
     }
 }
