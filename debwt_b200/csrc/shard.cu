@@ -427,9 +427,8 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         pc.tick("query_exchange");
         if (n_loc) {
             if (k_apply_in_queries(sk, n_loc, ki, gmask, qr, m_q, st)) return -1;
-            if (k_mark_heads_tails(W, d_seps, R, sk, n_loc, ki, gmask, st)) return -1;
-            if (k_propagate(sk, n_loc, gmask, st)) return -1;
-        }
+            if (k_mark_heads_tails(W, d_seps, R, sk, n_loc, ki, gmask, st)) return -1;      // (the masks reach the other members of
+        }                                                                                       //  their groups in k_branch_count)
         SCUDA(cudaStreamSynchronize(st));
         pool.rewind(mark);
         pc.tick("apply+propagate");
@@ -442,7 +441,7 @@ int shard_build_impl(debwt_shard* s, const void* slice, int slice_on_device, u64
         u64 h_tot[2] = {0, 0};
         if (n_loc) {
             if (pool.alloc(&brws, branch_workspace_bytes(n_loc))) return -1;
-            if (k_branch_count(sk, n_loc, gmask, false, brws, d_tot, st)) return -1;
+            if (k_branch_count(sk, n_loc, gmask, true, brws, d_tot, st)) return -1;
             SCUDA(cudaMemcpyAsync(h_tot, d_tot, 16, cudaMemcpyDeviceToHost, st));
             SCUDA(cudaStreamSynchronize(st));
         }
