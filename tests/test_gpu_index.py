@@ -107,3 +107,26 @@ def test_device_generators_match_numpy():
     t4, s4 = synth_gpu.config4(500_000, 4)
     w4, ws4 = api.join_records(synth.config4(500_000, 4))
     assert (t4.cpu().numpy() == w4).all() and (s4 == ws4).all()
+
+
+@pytest.mark.parametrize("kind", ["poly_a", "tandem", "two_copies"])
+def test_degenerate_repeats_invert(kind):
+    # one (k+1)-mer repeated more than 65 536 times in a row in the sorted keys: the target-tiled in-edge join leaves the tail of
+    # that run on its overflow list (mark_edges_over_kernel); long tandem repeats / whole-record copies: tie runs that K10 walks
+    # for thousands of codes.  Beyond what a CPU suffix sort does in seconds, so the check is the LF inversion on the GPU.
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    if kind == "poly_a":
+        recs = [np.concatenate([np.full(90_000, ord("A"), np.uint8), acgt[rng.integers(0, 4, 3000)]]),
+                np.concatenate([acgt[rng.integers(0, 4, 2000)], np.full(70_000, ord("A"), np.uint8), acgt[rng.integers(0, 4, 50)]])]
+    elif kind == "tandem":
+        unit = acgt[rng.integers(0, 4, 37)]
+        recs = [np.concatenate([np.tile(unit, 4000), acgt[rng.integers(0, 4, 500)]]), np.tile(unit, 1500)]
+    else:
+        a = acgt[rng.integers(0, 4, 120_000)]
+        recs = [a, a.copy(), a[:60_000].copy()]
+    text, seps = api.join_records(recs)
+    with api.BwtBuilder() as b:
+        b.set_records(recs)
+        b.build()
+        assert b.verify(text)[0] == 0
