@@ -626,15 +626,22 @@ __global__ void __launch_bounds__(TPB) branch_kernel(const u64* __restrict__ k, 
         if (lane == 0) { s_cnt[j * NW + warp] = __popc(bal[j]); s_blue[j * NW + warp] = sz; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                       // 64 partials: serial exclusive scan
-        u32 a = 0, b = 0;
-        for (int q = 0; q < BR_ITEMS * NW; ++q) {
-            const u32 ca = s_cnt[q], cb = s_blue[q];
-            s_cnt[q] = a; s_blue[q] = b;
-            a += ca; b += cb;
+    if (warp == 0) {                              // 64 partials: exclusive scan by the first warp, two per lane
+        static_assert(BR_ITEMS * NW == 64, "two partials per lane");
+        const u32 c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1], b0 = s_blue[2 * lane], b1 = s_blue[2 * lane + 1];
+        u32 ic = c0 + c1, ib = b0 + b1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 tc = __shfl_up_sync(0xffffffffu, ic, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ic += tc; ib += tb; }
         }
-        s_cnt[BR_ITEMS * NW] = a; s_blue[BR_ITEMS * NW] = b;
-        if (!WRITE) { tile_nb[blockIdx.x] = a; tile_blue[blockIdx.x] = b; }
+        const u32 ec = ic - (c0 + c1), eb = ib - (b0 + b1);
+        s_cnt[2 * lane] = ec; s_cnt[2 * lane + 1] = ec + c0;
+        s_blue[2 * lane] = eb; s_blue[2 * lane + 1] = eb + b0;
+        if (lane == 31) {
+            s_cnt[BR_ITEMS * NW] = ic; s_blue[BR_ITEMS * NW] = ib;
+            if (!WRITE) { tile_nb[blockIdx.x] = ic; tile_blue[blockIdx.x] = ib; }
+        }
     }
     if (!WRITE) return;
     __syncthreads();
