@@ -448,7 +448,7 @@ struct WorkItem {
 // whole item in shared memory), `huge` (first cut into tiny/small ones by split_kernel).  Counters live in
 // device memory: cnt[0] small, cnt[1] huge, cnt[2] tiny.
 constexpr int TINY = 512;
-constexpr int TINY_TPB = 128;
+constexpr int TINY_TPB = 64;
 struct WorkLists {
     WorkItem* small;
     WorkItem* huge;
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u
 // fallback (at most 32 R such entries exist).
 constexpr int SPLIT_MAX_BUCKETS = 256;
 constexpr int SPLIT_OVERSAMPLE = 8;
-constexpr int SPLIT_TARGET = 256;      // aimed-for bucket size (the tiny class)
+constexpr int SPLIT_TARGET = 256;      // aimed-for bucket size (128 measured the same)
 
 __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, SpView sp, const WorkItem* __restrict__ items,
                                                        const u32* __restrict__ n_items_ptr, WorkLists cur, WorkLists next,
@@ -898,7 +898,7 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
     if (n_big) {
         // round-based refinement of the segments beyond one warp's shared-memory slice
         auto refine_small = refine_kernel<BIG_TPB, CHUNK, 2>;
-        auto refine_tiny = refine_kernel<TINY_TPB, TINY, 8>;    // 8, 10 or 12 blocks per SM measured the same
+        auto refine_tiny = refine_kernel<TINY_TPB, TINY, 16>;    // 8, 10 or 12 blocks per SM measured the same
         static bool attr_done[64] = {};        // per device: function attributes belong to the device's context
         int cur_dev = 0;
         cudaGetDevice(&cur_dev);
@@ -941,7 +941,7 @@ int k_sort_blue(u64* blue, BranchTable bt, SpView sp, u32* d_work, cudaStream_t 
                 ++launched;
             }
             refine_small<<<148u * 2u, BIG_TPB, kChunkSmem, st>>>(blue, sp, cur.small, cur.cnt + 0, nxt, g_key, g_tag);
-            refine_tiny<<<148u * 8u, TINY_TPB, (size_t)TINY * 20, st>>>(blue, sp, cur.tiny, cur.cnt + 2, nxt, g_key, g_tag);
+            refine_tiny<<<148u * 16u, TINY_TPB, (size_t)TINY * 20, st>>>(blue, sp, cur.tiny, cur.cnt + 2, nxt, g_key, g_tag);
             launched += 2;
             u32 n_fin[8];
             CUDA_TRY(cudaMemcpyAsync(n_fin, d_cnt, 32, cudaMemcpyDeviceToHost, st));
