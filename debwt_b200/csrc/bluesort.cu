@@ -54,6 +54,18 @@ __device__ __forceinline__ u32 sep_window(const SpView& v, u64 s) {
     return fetch_sep(v, s);
 }
 
+// Code word of the window at s as an integer that sorts like the string among windows of one item: a window whose first
+// separator code is its t-th code is larger than every window that agrees on the t codes before it and has a base there, so its
+// word is filled with ones from code t on and `np` tells it apart from a plain word with the same value (plain first).
+// Windows with equal (word, np) are not ordered by this: plain ones tie on 32 codes, the others need the comparator.
+__device__ __forceinline__ u64 order_word(const SpView& v, u64 s, bool& np) {
+    u64 wd = text_window32(v.codes, s);
+    const u32 fs = sep_window(v, s);
+    np = fs != 0;
+    if (np) wd |= ~0ull >> (2 * (__ffs(fs) - 1));
+    return wd;
+}
+
 // strict "string at sa < string at sb" starting the comparison `skip` codes in; sa != sb
 __device__ __forceinline__ bool sp_less_from(const SpView& v, u64 sa, u64 sb, u32 skip) {
     sa += skip;
@@ -498,8 +510,9 @@ __global__ void __launch_bounds__(TPB) seed_items_kernel(BranchTable bt, const u
 // Entries are moved bucket by bucket (through `scratch`), every bucket becomes an item of its own: ordinary
 // buckets at the same depth (sorted by refine_kernel this round when they fit CHUNK, split again next round
 // otherwise), equality buckets at depth + 32.  O(len) traffic per item instead of the O(len log^2 len) of a
-// sorting network over HBM.  Items holding a word with a separator code are left to refine_kernel's comparator
-// fallback (at most 32 R such entries exist).
+// sorting network over HBM.  A window with a separator code is bucketed by order_word(): it lands where it belongs among
+// the plain windows, and only the small item it ends up in takes refine_kernel's comparator path (a huge item that holds one
+// such window used to go to the comparator network over HBM as a whole: 7 ms at 3.1 Gbp).
 constexpr int SPLIT_MAX_BUCKETS = 256;
 constexpr int SPLIT_OVERSAMPLE = 8;
 constexpr int SPLIT_TARGET = 256;      // aimed-for bucket size (128 measured the same)
@@ -527,7 +540,8 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
             u64 wd = ~0ull;
             if (t < m) {
                 const u64 e = ent[(u64)t * len / m];
-                wd = text_window32(sp.codes, (e >> 4) + depth);
+                bool np;
+                wd = order_word(sp, (e >> 4) + depth, np);
             }
             s_sample[t] = wd;
         }
@@ -549,22 +563,31 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
         for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
             const u64 e = ent[t];
             if ((u32)(e & 15ull) != prev0) s_mixed = 1;
-            const u64 sidx = (e >> 4) + depth;
-            const u64 wd = text_window32(sp.codes, sidx);
-            if (!(sep_window(sp, sidx) == 0 && sidx + 32 <= sp.n_codes)) s_flag = 1;
+            bool np;
+            const u64 wd = order_word(sp, (e >> 4) + depth, np);
             u32 lo = 0, hi = n_split;                       // first splitter >= wd
             while (lo < hi) {
                 const u32 mid = (lo + hi) >> 1;
                 if (s_split[mid] < wd) lo = mid + 1; else hi = mid;
             }
-            const u32 b = 2 * lo + ((lo < n_split && s_split[lo] == wd) ? 1u : 0u);
+            // equal to a splitter: the plain windows tie on 32 codes (equality bucket, 32 codes deeper next time); a window with a
+            // separator code sorts after them, i.e. first in the ordinary bucket that follows
+            const u32 b = 2 * lo + ((lo < n_split && s_split[lo] == wd) ? (np ? 2u : 1u) : 0u);
             atomicAdd(&s_hist[b], 1u);
             g_bucket[it.off + t] = b;
         }
         __syncthreads();
-        const bool fallback = s_flag != 0, mixed = s_mixed != 0;
+        const bool mixed = s_mixed != 0;
         if (!mixed) { __syncthreads(); continue; }          // every prev symbol equal: nothing to order
-        if (fallback) {                                     // separator inside a word: comparator path of refine_kernel
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (u32 b = 0; b < n_buckets; ++b) {
+                s_start[b] = run; s_pos[b] = run; run += s_hist[b];
+                if (s_hist[b] == len && !(b & 1u)) s_flag = 1;      // no progress: windows with separator codes that all tie
+            }
+        }
+        __syncthreads();
+        if (s_flag) {                                       // the comparator network of refine_kernel orders them
             if (threadIdx.x == 0) {
                 const u32 i = atomicAdd(cur.cnt + 0, 1u);
                 if (i < cur.cap_small) cur.small[i] = it;
@@ -572,11 +595,6 @@ __global__ void __launch_bounds__(BIG_TPB) split_kernel(u64* __restrict__ blue, 
             __syncthreads();
             continue;
         }
-        if (threadIdx.x == 0) {
-            u32 run = 0;
-            for (u32 b = 0; b < n_buckets; ++b) { s_start[b] = run; s_pos[b] = run; run += s_hist[b]; }
-        }
-        __syncthreads();
         // ---- pass 2: move the entries bucket by bucket ----
         for (u32 t = threadIdx.x; t < len; t += blockDim.x) {
             const u32 b = g_bucket[it.off + t];
