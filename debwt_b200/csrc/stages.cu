@@ -947,7 +947,7 @@ namespace {
 // hash-table probes of the positions that passed, four at a time (the straightforward loop kept one dependent read in
 // flight per thread and spent 60 % of its time waiting for the filter and the probe).  No block-wide compaction: the
 // candidates of a thread are a 16-bit mask.
-constexpr int FP_BATCH = 4;
+constexpr int FP_BATCH = 4;                // 8 measured slower (registers)
 __global__ void __launch_bounds__(TPB) flag_positions_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                             const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
                                                             u32* __restrict__ mo_bits, u64* __restrict__ blue) {
