@@ -490,28 +490,35 @@ constexpr u64 ME_TILE = 8192;
 constexpr u64 ME_CAP = 8 * ME_TILE;
 struct EdgeRun { u64 begin, end; };
 
+// bounds[c * (tiles + 1) + t] = first source of the c block whose target lies in tile t or later (one thread per bound, so that
+// the join's blocks start without a search and a barrier of their own)
+__global__ void __launch_bounds__(TPB) edge_bounds_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u64 tiles,
+                                                         u64* __restrict__ bounds) {
+    const u64 x = (u64)blockIdx.x * TPB + threadIdx.x;
+    if (x >= 4 * (tiles + 1)) return;
+    const u32 c = (u32)(x / (tiles + 1));
+    const u64 t = x % (tiles + 1);
+    const u64 cbeg = ki.idx[(u64)c << (ki.bits - 2)];
+    const u64 cend = (c == 3) ? n : (u64)ki.idx[(u64)(c + 1) << (ki.bits - 2)];
+    // sources whose query (X followed by A) sorts after key a - 1 and not after key b - 1 have their lower bound in [a, b)
+    const u64 a = t * ME_TILE;
+    u64 r;
+    if (a == 0) r = cbeg;
+    else if (a >= n) r = cend;
+    else {
+        const u64 low = (k[a - 1] >> 2) + 1;
+        r = (low >> 62) ? cend : indexed_lower_bound(k, ki, ((u64)c << 62) | low);
+    }
+    bounds[x] = r;
+}
+
 __global__ void __launch_bounds__(TPB) mark_edges_kernel(const u64* __restrict__ k, u64 n, KeyIndex ki, u16* __restrict__ gmask,
-                                                        EdgeRun* __restrict__ over, u32* __restrict__ n_over) {
-    __shared__ u64 s_rng[2];
+                                                        const u64* __restrict__ bounds, u64 tiles, EdgeRun* __restrict__ over,
+                                                        u32* __restrict__ n_over) {
     const u32 c = blockIdx.x & 3u;
     const u64 tile = blockIdx.x >> 2;
-    if (threadIdx.x < 2) {
-        const u64 cbeg = ki.idx[(u64)c << (ki.bits - 2)];
-        const u64 cend = (c == 3) ? n : (u64)ki.idx[(u64)(c + 1) << (ki.bits - 2)];
-        // sources whose query (X followed by A) sorts after key a - 1 and not after key b - 1 have their lower bound in [a, b)
-        const u64 a = (tile + threadIdx.x) * ME_TILE;
-        u64 r;
-        if (a == 0) r = cbeg;
-        else if (a >= n) r = cend;
-        else {
-            const u64 low = (k[a - 1] >> 2) + 1;
-            r = (low >> 62) ? cend : indexed_lower_bound(k, ki, ((u64)c << 62) | low);
-        }
-        s_rng[threadIdx.x] = r;
-    }
-    __syncthreads();
-    const u64 sb = s_rng[0];
-    u64 se = s_rng[1];
+    const u64 sb = bounds[c * (tiles + 1) + tile];
+    u64 se = bounds[c * (tiles + 1) + tile + 1];
     if (se - sb > ME_CAP && se > sb) {
         if (threadIdx.x == 0) over[atomicAdd(n_over, 1u)] = EdgeRun{sb + ME_CAP, se};
         se = sb + ME_CAP;
@@ -730,13 +737,15 @@ int k_mark_edges(const u64* sorted, u64 n, KeyIndex ki, u16* gmask, cudaStream_t
     const u64 tiles = (n + ME_TILE - 1) / ME_TILE;
     const u64 cap = n / ME_CAP + 8;                          // runs that can exceed ME_CAP
     char* ws = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), 16 + cap * sizeof(EdgeRun), st));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&ws), 16 + cap * sizeof(EdgeRun) + 4 * (tiles + 1) * 8, st));
     u32* n_over = reinterpret_cast<u32*>(ws);
     EdgeRun* over = reinterpret_cast<EdgeRun*>(ws + 16);
+    u64* bounds = reinterpret_cast<u64*>(ws + 16 + cap * sizeof(EdgeRun));
     cudaMemsetAsync(n_over, 0, 16, st);
-    mark_edges_kernel<<<(unsigned)(4 * tiles), TPB, 0, st>>>(sorted, n, ki, gmask, over, n_over);
+    edge_bounds_kernel<<<grid_for(4 * (tiles + 1), TPB), TPB, 0, st>>>(sorted, n, ki, tiles, bounds);
+    mark_edges_kernel<<<(unsigned)(4 * tiles), TPB, 0, st>>>(sorted, n, ki, gmask, bounds, tiles, over, n_over);
     mark_edges_over_kernel<<<148 * 8, TPB, 0, st>>>(sorted, n, ki, gmask, over, n_over);
-    DEBWT_COUNT(2);
+    DEBWT_COUNT(3);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(ws, st);
     if (e != cudaSuccess) { set_error(std::string("mark_edges: ") + cudaGetErrorString(e)); return -1; }
