@@ -1080,7 +1080,7 @@ constexpr int FK_UNROLL = 4;
 __global__ void __launch_bounds__(TPB) flag_positions_keys_kernel(const u64* __restrict__ words, u64 nwords_total, u64 n,
                                                                  const u64* __restrict__ seps, u64 n_rec, BranchTable bt,
                                                                  int shift, u32* __restrict__ mo_bits, u64* __restrict__ bkeys,
-                                                                 unsigned long long* __restrict__ counter, int dbg_stop) {
+                                                                 unsigned long long* __restrict__ counter) {
     __shared__ TileText t;
     __shared__ u64 s_keys[TILE_POS];
     __shared__ u16 s_hits[TILE_POS];
@@ -1126,7 +1126,6 @@ __global__ void __launch_bounds__(TPB) flag_positions_keys_kernel(const u64* __r
             fw[j] = ok ? (__ldg(filter + (f >> 5)) >> (f & 31)) & 1u : 0u;
         }
     }
-    if (dbg_stop == 1) { u32 a = 0; for (int j = 0; j < TILE_ROWS; ++j) a += fw[j]; if (a == 77777u) mo_bits[0] = a; return; }
     // ---- (B) compact the positions that passed ----
 #pragma unroll
     for (int j = 0; j < TILE_ROWS; ++j) {
@@ -1149,7 +1148,6 @@ __global__ void __launch_bounds__(TPB) flag_positions_keys_kernel(const u64* __r
     }
     __syncthreads();
     // ---- (C) branch-table lookups of the listed positions, FK_UNROLL per thread at a time ----
-    if (dbg_stop == 2) return;
     const u32 nh = s_nhits;
     const u64 hmask = (1ull << bt.hbits) - 1;
     for (u32 c0 = 0; c0 < nh; c0 += TPB * FK_UNROLL) {
@@ -1305,9 +1303,8 @@ int k_flag_positions(const u64* words, u64 n, const u64* d_seps, u64 n_rec, Bran
 
 int k_flag_positions_keys(const u64* words, u64 n, const u64* d_seps, u64 n_rec, BranchTable bt, int shift, u32* mo_bits,
                           u64* bkeys, u64* d_counter, cudaStream_t st) {
-    static const int dbg_stop = getenv("DEBWT_FK_STOP") ? atoi(getenv("DEBWT_FK_STOP")) : 0;
     flag_positions_keys_kernel<<<grid_for(n, TILE_POS), TPB, 0, st>>>(words, text_words(n), n, d_seps, n_rec, bt, shift, mo_bits, bkeys,
-                                                                      reinterpret_cast<unsigned long long*>(d_counter), dbg_stop);
+                                                                      reinterpret_cast<unsigned long long*>(d_counter));
     DEBWT_COUNT(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -2,9 +2,10 @@
 
 The device sorts the blue entries of one multi-in k-mer by the branch-code string that starts at their spIndex
 (reference: src/sortBlue.c:76-280, cmpSP :109-173).  It never compares strings pairwise on large segments: it refines
-runs of entries 32 codes (one u64 word) at a time -- sample-sort split of huge items with equality buckets, a three-way
-peel around a dominant word, an integer sort on plain words, direct comparisons only for short runs, a comparator
-fallback when a word holds a separator code.  This file restates that control flow in plain Python with scaled-down
+runs of entries one code word at a time -- sample-sort split of everything above the tiny class with equality buckets (a
+window with a separator code is bucketed by an order-preserving word, order_word()), a three-way peel around a dominant
+word, a packed network on the first 27 codes of plain words, direct comparisons only for short runs, a comparator fallback
+when a small item holds a separator code.  This file restates that control flow in plain Python with scaled-down
 thresholds and checks it against `sorted()` on the code strings, so the host-visible logic (what becomes an item, at
 which depth, when a run is finished) is pinned on CPU; the CUDA kernels are checked against the oracle in
 tests/test_gpu_parity.py.
@@ -13,8 +14,9 @@ import random
 
 import pytest
 
-CHUNK = 64          # device: 4096   largest item handled without the split
+SPLIT_ABOVE = 16    # device: 512    items above this are cut by the split first
 SHORT = 4           # device: 32     runs up to this size are ranked by direct comparisons
+ADV = 27            # device: 27     codes the packed network of refine_kernel<.., 512> compares per step
 SPLIT_TARGET = 8    # device: 256
 MAX_BUCKETS = 8     # device: 256
 OVERSAMPLE = 2      # device: 8
@@ -40,6 +42,18 @@ class Codes:
             val = (val << 2) | min(c, 3)
         return val, plain
 
+    def order_word(self, s, depth):
+        """(word with ones from the first separator code on, has-a-separator flag): debwt::order_word"""
+        p = s + depth
+        chunk = self.syms[p:p + W]
+        val, np_ = 0, False
+        for i in range(W):
+            c = chunk[i] if i < len(chunk) else 5
+            if c >= 4:
+                np_ = True
+            val = (val << 2) | (3 if np_ else c)
+        return val, np_
+
     def less(self, a, b):
         return self.syms[a:] < self.syms[b:]
 
@@ -58,7 +72,7 @@ def refine_segment(entries, codes, stats=None):
         nxt = []
         cur = []
         for off, ln, depth in items:            # split_kernel: huge items are cut before the round's refinement
-            if ln > CHUNK:
+            if ln > SPLIT_ABOVE:
                 _split(ent, codes, off, ln, depth, cur, nxt, stats)
             else:
                 cur.append((off, ln, depth))
@@ -80,29 +94,30 @@ def _full_sort(ent, codes, off, ln):
 
 def _split(ent, codes, off, ln, depth, cur, nxt, stats):
     seg = ent[off:off + ln]
-    words = [codes.word(e >> 4, depth) for e in seg]
+    words = [codes.order_word(e >> 4, depth) for e in seg]
     if not _mixed(ent, off, ln):
-        return
-    if not all(p for _, p in words):            # separator inside a word: comparator fallback on the whole item
-        stats["fallback"] = stats.get("fallback", 0) + 1
-        _full_sort(ent, codes, off, ln)
         return
     nb = max(2, min(MAX_BUCKETS, -(-ln // SPLIT_TARGET)))
     m = nb * OVERSAMPLE
     sample = sorted(words[t * ln // m][0] for t in range(m))
     split = [sample[t * OVERSAMPLE + OVERSAMPLE - 1] for t in range(nb - 1)]
     buckets = [[] for _ in range(2 * nb - 1)]
-    for e, (w, _) in zip(seg, words):
+    for e, (w, np_) in zip(seg, words):
         lo = sum(1 for s in split if s < w)      # first splitter >= w
-        b = 2 * lo + (1 if lo < len(split) and split[lo] == w else 0)
+        # equal to a splitter: plain windows tie on 32 codes (equality bucket); one with a separator code sorts after them
+        b = 2 * lo + ((2 if np_ else 1) if lo < len(split) and split[lo] == w else 0)
         buckets[b].append(e)
+    if any(len(members) == ln and not b & 1 for b, members in enumerate(buckets)):
+        stats["fallback"] = stats.get("fallback", 0) + 1      # no progress: separator windows that all tie -> comparator
+        _full_sort(ent, codes, off, ln)
+        return
     pos = off
     stats["splits"] = stats.get("splits", 0) + 1
     for b, members in enumerate(buckets):
         ent[pos:pos + len(members)] = members
         if len(members) >= 2:
             item = (pos, len(members), depth + (W if b & 1 else 0))
-            (nxt if len(members) > CHUNK else cur).append(item)
+            (nxt if len(members) > SPLIT_ABOVE else cur).append(item)      # still long: cut again next round
         pos += len(members)
 
 
@@ -139,7 +154,8 @@ def _refine_item(ent, codes, off, ln, depth, nxt, stats):
                         _rank_short(ent, codes, o, len(part))
                 lo, vlen, depth, peels = lo + len(lt), len(eq), depth + W, peels + 1
                 continue
-        order = sorted(range(vlen), key=lambda t: vals[t])          # the network: integer sort on the words
+        vals = [v >> (2 * (W - ADV)) for v in vals]                  # the packed network: the first ADV codes | index
+        order = sorted(range(vlen), key=lambda t: (vals[t], t))
         seg = [ent[lo + t] for t in order]
         vals = [vals[t] for t in order]
         ent[lo:lo + vlen] = seg
@@ -151,7 +167,7 @@ def _refine_item(ent, codes, off, ln, depth, nxt, stats):
             size = t + 1 - h
             if size >= 2 and _mixed(ent, lo + h, size):
                 if size > SHORT:
-                    nxt.append((lo + h, size, depth + W))
+                    nxt.append((lo + h, size, depth + ADV))
                 else:
                     _rank_short(ent, codes, lo + h, size)
             h = t + 1
@@ -200,8 +216,26 @@ def test_refinement_model_orders_like_string_sort(seed, n_codes, n_entries, fami
     assert [e & 15 for e in got] == [e & 15 for e in want]
     assert sorted(got) == sorted(entries)
     if family and family[2] <= 1 and not seps:
-        assert stats.get("peels", 0) > 0
-    if n_entries > CHUNK and not seps:
+        assert stats.get("peels", 0) > 0 or stats["rounds"] > 5      # deep ties: peeled, or cut again 32 codes deeper per round
+    if n_entries > SPLIT_ABOVE:
         assert stats.get("splits", 0) > 0
     if seps:
         assert stats.get("fallback", 0) > 0
+
+
+def test_order_word_is_consistent_with_the_comparator():
+    """split_kernel buckets by (order_word, has-separator): whenever that pair differs, it must order two windows like cmpSP"""
+    rng = random.Random(9)
+    for trial in range(300):
+        n = 200
+        syms = [rng.randrange(2) * 3 for _ in range(n)]            # only A and T: long common prefixes, all-T tails
+        for _ in range(rng.randrange(1, 12)):
+            syms[rng.randrange(n - 1)] = 4
+        syms[-1] = 5
+        codes = Codes(syms)
+        starts = rng.sample(range(n - 1), 40)
+        keyed = [(codes.order_word(s, 0), s) for s in starts]
+        for (ka, a) in keyed:
+            for (kb, b) in keyed:
+                if ka < kb:
+                    assert codes.less(a, b), (trial, a, b)
