@@ -11,12 +11,15 @@
 //   <= 32   : one warp, entries in registers, rank by counting;
 //   <= 128  : one warp, entries + cached words in shared memory, same-direction bitonic network;
 //   larger  : round-based refinement (MSD style) driven by work lists: a work item is a run of entries that
-//             agree on their first `depth` codes; one block sorts it by the next 32 codes with a network whose
-//             comparisons touch no memory (<= 4096 entries entirely in shared memory; beyond that every
-//             aligned 4096-entry block is staged once per merge level and only the long-distance stages run
-//             over HBM); equal-word runs that still hold two prev symbols are finished by direct comparisons
+//             agree on their first `depth` codes.  Items above 512 entries are cut by a sample-sort split on their code
+//             word at `depth` (up to 256 buckets, equality buckets advance 32 codes; a window with a separator code is
+//             bucketed by an order-preserving word, order_word()); items of at most 512 entries are sorted in shared
+//             memory by a packed network (one u64 = 27 codes | index, two network stages per pass) whose comparisons
+//             touch no memory; equal-word runs that still hold two prev symbols are finished by direct comparisons
 //             (<= 32 entries) or become the next round's items, so long common prefixes are walked once per
-//             entry instead of once per comparison and the work shrinks geometrically.
+//             entry instead of once per comparison and the work shrinks geometrically.  Items that hold a separator
+//             code take a comparator network (in shared memory, or over HBM with 4096-entry blocks staged per merge level
+//             when a whole long item ties on such windows).
 // The network uses virtual +inf padding (all compare-exchanges point the same way), so no segment
 // needs scratch for padding.  Segments whose prev symbols are all equal are skipped
 // (src/sortBlue.c:192-219): any order gives the same BWT.
