@@ -11,7 +11,15 @@ rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if "# Samples" in r][0]
 hdr = rows[hi]
 iL, iS, iN, iE = 0, 1, hdr.index("# Samples"), hdr.index("Instructions Executed")
-iW, iG = hdr.index("L1 Wavefronts Shared"), hdr.index("L2 Theoretical Sectors Global")
+def col(name):                      # a kernel without shared memory / global accesses has no such column
+    return hdr.index(name) if name in hdr else None
+
+
+iW, iG = col("L1 Wavefronts Shared"), col("L2 Theoretical Sectors Global")
+
+
+def val(r, i):
+    return int(r[i]) if i is not None and r[i] not in ("", "n/a") else 0
 fname = ""
 lines = []
 for r in rows[:hi] + rows[hi + 1:]:
@@ -21,10 +29,10 @@ for r in rows[:hi] + rows[hi + 1:]:
         lines.append((fname, r))
 tot = sum(int(r[iN]) for _, r in lines) or 1
 tote = sum(int(r[iE]) for _, r in lines) or 1
-totw = sum(int(r[iW]) for _, r in lines) or 1
-totg = sum(int(r[iG]) for _, r in lines) or 1
+totw = sum(val(r, iW) for _, r in lines) or 1
+totg = sum(val(r, iG) for _, r in lines) or 1
 print(f"samples {tot}, warp instructions {tote}, shared wavefronts {totw}, L2 sectors {totg}")
 print("  smp%   ins%  smem%    L2%  line")
 for f, r in sorted(lines, key=lambda t: -int(t[1][iN]))[:top]:
-    print(f"{100 * int(r[iN]) / tot:5.1f}  {100 * int(r[iE]) / tote:5.1f}  {100 * int(r[iW]) / totw:5.1f}  {100 * int(r[iG]) / totg:5.1f}  "
+    print(f"{100 * int(r[iN]) / tot:5.1f}  {100 * int(r[iE]) / tote:5.1f}  {100 * val(r, iW) / totw:5.1f}  {100 * val(r, iG) / totg:5.1f}  "
           f"{f}:{r[iL]}  {r[iS].strip()[:100]}")
